@@ -1,0 +1,201 @@
+/*
+ * softray_cuda.h -- C ABI of libsoftray_cuda.so, the B200 (sm_100a) drop-in for SoftRay's
+ * per-pixel raytrace hot path.
+ *
+ * The reference (voidstar69/softray, C#) has no FFI today.  The seam this library plugs into is
+ * the private frame driver  Renderer.RaytraceGeometry(Instance)  (Engine3D/Renderer.cs:1501-1687):
+ * everything after PreCalculate() (:1531) -- decorator chain, row blocks, RaytraceBlock,
+ * TraceRayComplex/TraceRaySimple, IRayIntersectable.IntersectRay, Surface.DrawPixel -- becomes one
+ * P/Invoke to softray_render().  See INTEGRATION.md for the C# binding.
+ *
+ * Conventions
+ *   - plain C, POD structs, natural alignment (every struct below is free of padding surprises:
+ *     8-byte members first or explicitly padded), no callbacks, no C++ types, no torch types.
+ *   - every entry point returns SOFTRAY_OK (0) or a negative SOFTRAY_E_* code; nothing throws or
+ *     aborts across the boundary.  softray_last_error() gives a UTF-8 message for the last failure
+ *     on that context (or the process-wide last error when ctx is NULL).
+ *   - the caller owns every pointer it passes; scene_create copies; render writes only
+ *     pixels/hit_ids/stats.
+ *   - one in-flight call per softray_ctx ("Not multithread safe!", Renderer.cs:1498); distinct
+ *     contexts are independent (one context per GPU / per process rank).
+ *   - NO CPU FALLBACK: without a CUDA device softray_create fails with SOFTRAY_E_NO_DEVICE.
+ *   - pixel format: 0xAARRGGBB in a little-endian uint32 (Surface.cs:98-101), row-major,
+ *     index y*width+x (Surface.cs:179).
+ */
+#ifndef SOFTRAY_CUDA_H
+#define SOFTRAY_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOFTRAY_ABI_VERSION 1
+
+/* ---- error codes (map back to the .NET exceptions the reference throws) ------------------- */
+#define SOFTRAY_OK                     0
+#define SOFTRAY_E_INVALID_ARG        (-1)  /* ArgumentNullException / ArgumentOutOfRangeException   */
+#define SOFTRAY_E_VERTEX_OUTSIDE_BBOX (-2) /* "A triangle vertex is outside the bounding box",
+                                              SpatialSubdivision.cs:285-295                          */
+#define SOFTRAY_E_NO_DEVICE          (-3)  /* no CUDA device: there is no CPU fallback               */
+#define SOFTRAY_E_CUDA               (-4)  /* a CUDA runtime call failed                             */
+#define SOFTRAY_E_OOM                (-5)  /* host or device allocation failed                       */
+#define SOFTRAY_E_UNSUPPORTED        (-6)  /* a flag combination this path does not implement
+                                              (voxels, light fields, AO, path tracing, static
+                                              shadow cache: they stay on the managed path)          */
+#define SOFTRAY_E_FORMAT             (-7)  /* FormatException from the 3DS loader (Model.cs:555)     */
+
+typedef struct softray_ctx   softray_ctx;    /* opaque: one CUDA device, its streams and buffers     */
+typedef struct softray_scene softray_scene;  /* opaque: device-resident SoA geometry + BVHs          */
+
+/* ---- context -------------------------------------------------------------------------------- */
+
+/* device_ordinal: CUDA device index (a torchrun rank passes LOCAL_RANK).  Replaces nothing in
+ * the reference (it has no device); lifetime = where Renderer caches geometry_simple /
+ * geometry_subdivided / rootGeometry (Renderer.cs:173-175) and Renderer.Dispose (:236-255). */
+int  softray_create(int32_t device_ordinal, softray_ctx** out);
+void softray_destroy(softray_ctx* ctx);
+const char* softray_last_error(const softray_ctx* ctx);
+int  softray_abi_version(void);
+
+/* ---- scene: Model -> SoA triangles (+BVH), ExtraGeometryToRaytrace -> SoA spheres ------------ */
+
+/* One Model after PostProcessGeometry (Model.cs:750-831): vertices already in the unit cube.
+ * Triangle i keeps its position in Model.Triangles => IntersectionInfo.triIndex
+ * (Renderer.cs:1452-1469).  tri_argb[i] = Surface.PackColorAndAlpha(tri.diffuseMaterial, 1.0)
+ * (Renderer.cs:1463, Surface.cs:131-138).  bbox = Model.Min/Max (Renderer.cs:1487). */
+typedef struct softray_mesh {
+    const double*   verts_xyz;   /* n_verts * 3                                                    */
+    const int32_t*  tri_vidx;    /* n_tris * 3 (vertexIndex1..3, Model.cs:44-46)                   */
+    const uint32_t* tri_argb;    /* n_tris, alpha must be 0xFF (Triangle.cs:31)                    */
+    int32_t         n_verts;
+    int32_t         n_tris;
+    double          bbox_min[3];
+    double          bbox_max[3];
+} softray_mesh;
+
+/* Raytrace.Sphere(center, radius){Color} (Sphere.cs:25-32,50-54); argb = Color.ToARGB()
+ * (Color.cs:105-111). */
+typedef struct softray_sphere {
+    double   cx, cy, cz, r;
+    uint32_t argb;
+    uint32_t _pad;
+} softray_sphere;
+
+#define SOFTRAY_ACCEL_BVH    0   /* library-built BVHs (default); results identical to brute force  */
+#define SOFTRAY_ACCEL_BRUTE  1   /* linear scan of every primitive per ray, like
+                                    GeometryCollection.IntersectRay (GeometryCollection.cs:44-69)   */
+
+typedef struct softray_scene_desc {
+    const softray_mesh*   meshes;     int32_t n_meshes;   int32_t accel;  /* SOFTRAY_ACCEL_*       */
+    /* ExtraGeometryToRaytrace (Renderer.cs:460,1545-1549): tested BEFORE the mesh, so a sphere
+     * wins an exact rayFrac tie against a triangle (GeometryCollection.cs:53). */
+    const softray_sphere* spheres;    int32_t n_spheres;  int32_t _pad;
+} softray_scene_desc;
+
+/* Replaces MakeRayTracableGeometry_simple/_subdivided (Renderer.cs:1452-1494) + the Triangle
+ * ctor precompute (Triangle.cs:29-57) + the SpatialSubdivision ctor (SpatialSubdivision.cs:267-315,
+ * including its vertex-inside-bbox check).  Deterministic: the same input gives a bit-identical
+ * device layout on every call. */
+int  softray_scene_create(softray_ctx* ctx, const softray_scene_desc* desc, softray_scene** out);
+void softray_scene_destroy(softray_scene* scene);
+
+/* Layout fingerprint (FNV-1a over every device-resident scene buffer, in upload order) --
+ * the "bit-identical layout across runs" check. */
+int  softray_scene_fingerprint(const softray_scene* scene, uint64_t* out);
+
+/* ---- frame ---------------------------------------------------------------------------------- */
+
+/* Instance (Instance.cs): the C# side passes the matrices it already builds in InitRender
+ * (Instance.cs:134-135) so sin/cos stay .NET's.  Row-major 4x4, M[row*4+col]. */
+typedef struct softray_instance {
+    double  M[16];      /* _transform        = T(pos) * Roll * Pitch * Yaw                          */
+    double  Minv[16];   /* _inverseTransform = Yaw(-) * Pitch(-) * Roll(-) * T(-pos)                */
+    double  pos[3];     /* Instance.Position (view space)                                           */
+    int32_t mesh_id;    /* index into softray_scene_desc.meshes                                     */
+    int32_t _pad;
+} softray_instance;
+
+typedef struct softray_frame {
+    /* lighting, view space (Renderer.cs:38-41,207-217) */
+    double  ambient;                 /* ambientLight_intensity        (0.1)                        */
+    double  shininess;               /* specularLight_shininess       (100)                        */
+    double  light_dir_view[3];       /* directionalLight_dir          (normalise(-1,-1,1))         */
+    double  light_pos_view[3];       /* positionalLight_pos           ((0,0,1.5) - 2*dir)          */
+    double  fov_depth;               /* fieldOfViewDepth = 0.5/tan(22.5 deg) (Renderer.cs:97-101)  */
+    double  focal_depth;             /* rayTraceFocalDepth            (1.5)                        */
+    double  focal_strength;          /* rayTraceFocalBlurStrength     (10.0)                       */
+    const softray_instance* instances;  /* n_instances == 1: reference semantics of
+                                           RaytraceGeometry(instance).  > 1: nearest hit across
+                                           instances (extension)       */
+    int32_t n_instances;
+    int32_t width, height;           /* SetRenderingSurface (Renderer.cs:593-626)                  */
+    int32_t start_row, end_row;      /* rayTraceStartRow/EndRow, inclusive, clamped like :1652-1653;
+                                        exactly these rows are written         */
+    int32_t sub_pixel_res;           /* rayTraceSubPixelRes           (1)                          */
+    int32_t focal_blur;              /* rayTraceFocalBlur; only acts when sub_pixel_res > 1        */
+    int32_t subdivision;             /* rayTraceSubdivision (true): the mesh is traced through the
+                                        root-box clip of SpatialSubdivision.IntersectRay (:389-416) */
+    int32_t shading;                 /* rayTraceShading               (true)                       */
+    int32_t shadows;                 /* rayTraceShadows, dynamic mode (false)                      */
+    int32_t shadow_samples;          /* softShadowQuality             (100, ShadowMethod.cs:9)     */
+    int32_t point_lighting;          /* pointLighting                 (true)                       */
+    int32_t specular_lighting;       /* specularLighting              (true)                       */
+    int32_t random_seed;             /* rayTraceRandomSeed            (1234567890)                 */
+    uint32_t background_argb;        /* BackgroundColor; written as bg | 0xFF000000 (:1860)        */
+    /* extensions, 0 = reference behaviour */
+    int32_t reflection_depth;        /* mirror bounces, 0..4                                       */
+    int32_t texture3d_id;            /* 0 none, 1 = procedural "marble" Texture3D<byte>            */
+    int32_t _pad;
+} softray_frame;
+
+/* Counters (the reference's NumRaysFired / NumGeometryTests / NumNodeVisits, Renderer.cs:465-587)
+ * and device timings of the last render. */
+typedef struct softray_stats {
+    uint64_t rays_primary;     /* camera rays                                                      */
+    uint64_t rays_shadow;      /* ShadowMethod.TraceRaysForSoftShadows rays                        */
+    uint64_t rays_secondary;   /* reflection rays (extension)                                      */
+    uint64_t node_visits;      /* BVH nodes popped                                                 */
+    uint64_t prim_tests;       /* exact (reference-arithmetic) sphere + triangle tests             */
+    uint64_t prim_filter_tests;/* conservative FP32 pre-tests                                      */
+    uint64_t hits_primary;     /* camera rays that hit geometry                                    */
+    uint64_t launches;         /* kernels launched by this call                                    */
+    double   ms_kernel;        /* CUDA-event time of the render kernel(s)                          */
+    double   ms_h2d;           /* frame constants upload                                           */
+    double   ms_d2h;           /* framebuffer (+hit ids) readback                                  */
+    double   ms_total;         /* host wall time of the call                                       */
+} softray_stats;
+
+/* Host-buffer entry point: the drop-in for the body of Renderer.RaytraceGeometry.
+ *   pixels_argb : host, width*height uint32, caller-owned (C# pins surface.Pixels with `fixed`);
+ *                 only rows [start_row,end_row] are written.
+ *   hit_ids     : optional host width*height int32: triIndex >= 0 (flattened over meshes /
+ *                 instances: see DESIGN.md), -1 miss, <= -2 means sphere index -(id+2).
+ *                 With sub_pixel_res > 1 it records the LAST sub-ray of the pixel.
+ *   stats       : optional. */
+int  softray_render(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
+                    uint32_t* pixels_argb, int32_t* hit_ids, softray_stats* stats);
+
+/* Device-buffer entry point (the timed "inputs already resident" path and the multi-GPU path:
+ * the band stays in HBM for the NCCL gather).  d_pixels/d_hit_ids are device pointers on the
+ * context's device with the same full-frame indexing; `stream` is a cudaStream_t (0 = the
+ * context's own stream).  Asynchronous with respect to the host unless stats != NULL. */
+int  softray_render_device(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
+                           uint32_t* d_pixels_argb, int32_t* d_hit_ids, void* stream,
+                           softray_stats* stats);
+
+/* ---- helpers that mirror small reference functions the shim would otherwise re-implement ---- */
+
+/* Instance.InitRender matrices (Instance.cs:134-135, Matrix.cs:74-168), computed with the C
+ * library's sin/cos.  A C# host should pass its own matrices instead. */
+void softray_instance_init(softray_instance* inst, const double pos[3],
+                           double yaw, double pitch, double roll, int32_t mesh_id);
+
+/* Renderer() constructor defaults (Renderer.cs:207-230,70-85) for a width x height surface. */
+void softray_frame_defaults(softray_frame* frame, int32_t width, int32_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFTRAY_CUDA_H */
