@@ -32,6 +32,8 @@ extern "C" {
 #endif
 
 #define SOFTRAY_ABI_VERSION 1
+#define SOFTRAY_MAX_INSTANCES 128   /* instances per frame (composite extension) */
+#define SOFTRAY_MAX_SHADOW_SAMPLES 1024
 
 /* ---- error codes (map back to the .NET exceptions the reference throws) ------------------- */
 #define SOFTRAY_OK                     0
@@ -58,6 +60,9 @@ int  softray_create(int32_t device_ordinal, softray_ctx** out);
 void softray_destroy(softray_ctx* ctx);
 const char* softray_last_error(const softray_ctx* ctx);
 int  softray_abi_version(void);
+/* sizeof of the PODs below as this library was compiled: 0 mesh, 1 sphere, 2 scene_desc,
+ * 3 instance, 4 frame, 5 stats (a binding checks its own layout against these). */
+int  softray_abi_sizeof(int32_t which);
 
 /* ---- scene: Model -> SoA triangles (+BVH), ExtraGeometryToRaytrace -> SoA spheres ------------ */
 
@@ -147,7 +152,13 @@ typedef struct softray_frame {
     /* extensions, 0 = reference behaviour */
     int32_t reflection_depth;        /* mirror bounces, 0..4                                       */
     int32_t texture3d_id;            /* 0 none, 1 = procedural "marble" Texture3D<byte>            */
-    int32_t _pad;
+    /* row-band partition of [start_row,end_row] (the reference's row blocks, Renderer.cs:1659-1670,
+     * made explicit for one-process-per-GPU rendering): with band_count > 1 only the rows with
+     * ((row - start_row) / band_height) % band_count == band_index are traced and written.
+     * band_count <= 1 (or band_height <= 0) means every row. */
+    int32_t band_height;
+    int32_t band_count;
+    int32_t band_index;
 } softray_frame;
 
 /* Counters (the reference's NumRaysFired / NumGeometryTests / NumNodeVisits, Renderer.cs:465-587)
@@ -158,8 +169,9 @@ typedef struct softray_stats {
     uint64_t rays_secondary;   /* reflection rays (extension)                                      */
     uint64_t node_visits;      /* BVH nodes popped                                                 */
     uint64_t prim_tests;       /* exact (reference-arithmetic) sphere + triangle tests             */
-    uint64_t prim_filter_tests;/* conservative FP32 pre-tests                                      */
+    uint64_t sphere_tests;     /* of prim_tests, the ray/sphere ones                               */
     uint64_t hits_primary;     /* camera rays that hit geometry                                    */
+    uint64_t shaded_hits;      /* hits that went through shading (primary + reflection hits)       */
     uint64_t launches;         /* kernels launched by this call                                    */
     double   ms_kernel;        /* CUDA-event time of the render kernel(s)                          */
     double   ms_h2d;           /* frame constants upload                                           */
@@ -184,6 +196,26 @@ int  softray_render(softray_ctx* ctx, const softray_scene* scene, const softray_
 int  softray_render_device(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
                            uint32_t* d_pixels_argb, int32_t* d_hit_ids, void* stream,
                            softray_stats* stats);
+
+/* ---- multi-GPU: peer-mapped framebuffer --------------------------------------------------------
+ * One process per GPU renders its row bands (softray_frame.band_*) of the SAME frame.  The
+ * reference's analogue is the row-block fan-out inside one process (Renderer.cs:1655-1680), where
+ * every task stores into the one shared surface.Pixels; here rank 0 owns the framebuffer in its
+ * HBM, exports it, and the other ranks map it over NVLink and pass the mapped pointer as
+ * d_pixels_argb to softray_render_device: the render kernel's own coalesced stores are the gather.
+ * (The unfused alternative -- render locally, then NCCL-gather the bands -- needs none of this.) */
+#define SOFTRAY_IPC_HANDLE_BYTES 64
+int  softray_device_alloc(softray_ctx* ctx, uint64_t bytes, void** d_ptr_out);   /* cudaMalloc'd base pointer */
+int  softray_device_free(softray_ctx* ctx, void* d_ptr);
+int  softray_ipc_export(softray_ctx* ctx, void* d_ptr /* from softray_device_alloc */, char handle[SOFTRAY_IPC_HANDLE_BYTES]);
+int  softray_ipc_open(softray_ctx* ctx, const char handle[SOFTRAY_IPC_HANDLE_BYTES], void** d_ptr_out);
+int  softray_ipc_close(softray_ctx* ctx, void* d_ptr);
+
+/* ---- diagnostics ------------------------------------------------------------------------------
+ * Measured FMA-issue peak of the context's device in TFLOP/s (FMA = 2 flops): the denominator of
+ * the FP-issue roofline bench.py reports (MEASURED_PEAKS.json has no FP32/FP64 vector figure).
+ * fp64 != 0 measures DFMA, else FFMA. */
+int  softray_measure_fma_peak(softray_ctx* ctx, int32_t fp64, double* tflops_out);
 
 /* ---- helpers that mirror small reference functions the shim would otherwise re-implement ---- */
 

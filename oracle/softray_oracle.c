@@ -206,6 +206,7 @@ void orc_frame_defaults(softray_frame* f, int32_t width, int32_t height)
     f->specular_lighting = 1;
     f->random_seed = 1234567890;
     f->background_argb = 0;
+    f->band_height = 0; f->band_count = 1; f->band_index = 0;
 }
 
 /* Matrix.Multiply3X3 / Instance.TransformDirection[Reverse] (Matrix.cs:34-41, Instance.cs:216-235) */
@@ -1363,7 +1364,7 @@ static void render_pixel(const rctx* x, int col, int row, uint32_t* pixels, int3
     const softray_frame* f = x->f;
     const int W = f->width, H = f->height, n = f->sub_pixel_res;
     const double aspect = (double)H / (double)W;           /* Renderer.cs:621 */
-    vec starts[64], dirs[64];
+    vec starts[SOFTRAY_MAX_INSTANCES], dirs[SOFTRAY_MAX_INSTANCES];
     const int32_t ni = x->n_ic;
     orc_hit ph; int32_t which = 0; int hit = 0;
     uint32_t out_color;
@@ -1375,7 +1376,7 @@ static void render_pixel(const rctx* x, int col, int row, uint32_t* pixels, int3
         out_color = trace_ray_complex(x, starts, dirs, f->reflection_depth, &ph, &which, &hit);
     } else {
         int sum_r = 0, sum_g = 0, sum_b = 0;
-        vec focal_pt[64];
+        vec focal_pt[SOFTRAY_MAX_INSTANCES];
         if (f->focal_blur) {
             vec dir_view = v3(-((double)col / W - 0.5), -((double)row / H - 0.5) * aspect, f->fov_depth);
             for (int32_t i = 0; i < ni; i++) {
@@ -1439,8 +1440,12 @@ static void* render_worker(void* arg)
         int top = j->start_row + u * j->block_h;
         /* the reference's last block runs blockHeight rows even past end_row (App. A #16); only
          * rows inside [start_row,end_row] are produced here */
-        for (int row = top; row < top + j->block_h && row <= j->end_row; row++)
+        for (int row = top; row < top + j->block_h && row <= j->end_row; row++) {
+            /* row-band partition (softray_frame.band_*): rows of other bands are left untouched */
+            if (j->f->band_count > 1 && j->f->band_height > 0 &&
+                ((row - j->start_row) / j->f->band_height) % j->f->band_count != j->f->band_index) continue;
             for (int col = 0; col < j->f->width; col++) render_pixel(&x, col, row, j->pixels, j->hit_ids, j->aux);
+        }
     }
     pthread_mutex_lock(&j->lock);
     j->total.rays_primary += c.rays_primary; j->total.rays_shadow += c.rays_shadow;
@@ -1457,15 +1462,16 @@ int orc_render(const orc_scene* s, const softray_frame* f, const orc_options* op
     orc_options o;
     if (opt) o = *opt; else orc_options_defaults(&o);
     if (!s || !f || !pixels_argb || !f->instances) return SOFTRAY_E_INVALID_ARG;
-    if (f->width <= 0 || f->height <= 0 || f->sub_pixel_res < 1 || f->n_instances < 1 || f->n_instances > 64)
+    if (f->width <= 0 || f->height <= 0 || f->sub_pixel_res < 1 || f->n_instances < 1 || f->n_instances > SOFTRAY_MAX_INSTANCES)
         return SOFTRAY_E_INVALID_ARG;
     if (f->shadows && f->shadow_samples < 1) return SOFTRAY_E_INVALID_ARG;
     if (f->reflection_depth < 0 || f->reflection_depth > 4) return SOFTRAY_E_INVALID_ARG;
+    if (f->band_count > 1 && (f->band_index < 0 || f->band_index >= f->band_count)) return SOFTRAY_E_INVALID_ARG;
     if (f->n_instances > 1 && (s->n_spheres > 0 || f->shadows || (f->focal_blur && f->sub_pixel_res > 1) || f->reflection_depth
                                || o.path_tracing))
         return SOFTRAY_E_UNSUPPORTED;
 
-    inst_ctx ic[64];
+    inst_ctx ic[SOFTRAY_MAX_INSTANCES];
     int32_t base = 0;
     for (int32_t i = 0; i < f->n_instances; i++) {
         const softray_instance* in = &f->instances[i];

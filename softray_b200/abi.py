@@ -106,7 +106,9 @@ class Frame(C.Structure):
         ("background_argb", C.c_uint32),
         ("reflection_depth", C.c_int32),
         ("texture3d_id", C.c_int32),
-        ("_pad", C.c_int32),
+        ("band_height", C.c_int32),
+        ("band_count", C.c_int32),
+        ("band_index", C.c_int32),
     ]
 
 
@@ -117,8 +119,9 @@ class Stats(C.Structure):
         ("rays_secondary", C.c_uint64),
         ("node_visits", C.c_uint64),
         ("prim_tests", C.c_uint64),
-        ("prim_filter_tests", C.c_uint64),
+        ("sphere_tests", C.c_uint64),
         ("hits_primary", C.c_uint64),
+        ("shaded_hits", C.c_uint64),
         ("launches", C.c_uint64),
         ("ms_kernel", C.c_double),
         ("ms_h2d", C.c_double),
@@ -134,7 +137,7 @@ class Stats(C.Structure):
         return self.rays_primary + self.rays_shadow + self.rays_secondary
 
 
-EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 168, "stats": 96}
+EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 176, "stats": 104}
 
 assert C.sizeof(Mesh) == EXPECTED_SIZES["mesh"]
 assert C.sizeof(Sphere) == EXPECTED_SIZES["sphere"]

@@ -1,0 +1,847 @@
+// sr_api.cu -- the C ABI of libsoftray_cuda.so (include/softray_cuda.h): context, scene flatten +
+// upload (replaces MakeRayTracableGeometry_* Renderer.cs:1452-1494, the Triangle ctor precompute
+// Triangle.cs:29-57 and the SpatialSubdivision ctor SpatialSubdivision.cs:267-315) and the frame
+// entry points (replace the body of Renderer.RaytraceGeometry, Renderer.cs:1501-1687).
+//
+// Host arithmetic that feeds reference-exact device code (triangle precompute, light / camera
+// transforms, area-light offsets) is written in plain double expressions in the reference's
+// evaluation order and this file is compiled with -ffp-contract=off, so no FMA is ever formed.
+// There is NO CPU rendering path here: every pixel comes from render_kernel (sr_render.cu).
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/softray_cuda.h"
+#include "sr_bvh.h"
+#include "sr_types.h"
+
+namespace sr {
+cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets,
+                          uint32_t* d_pixels, int32_t* d_ids, unsigned int* d_tile_counter, DevCounters* d_counters,
+                          int grid_blocks, cudaStream_t stream);
+int render_kernel_occupancy(int smem_bytes);
+cudaError_t measure_fma_peak(bool fp64, int sm_count, cudaStream_t stream, double* tflops);
+}  // namespace sr
+
+using namespace sr;
+
+// ---------------------------------------------------------------------------------------------
+// opaque handles
+// ---------------------------------------------------------------------------------------------
+struct softray_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_staged = nullptr;   // the last frame's constants have left the pinned staging
+    bool staging_busy = false;
+    // per-frame device scratch (sized for SOFTRAY_MAX_INSTANCES / SOFTRAY_MAX_SHADOW_SAMPLES)
+    DevInstance* d_insts = nullptr;
+    double* d_offsets = nullptr;
+    unsigned int* d_tile_counter = nullptr;
+    DevCounters* d_counters = nullptr;
+    // pinned host staging for the frame constants and the counters
+    DevInstance* h_insts = nullptr;
+    double* h_offsets = nullptr;
+    DevCounters* h_counters = nullptr;
+    // device framebuffer of the host-buffer entry point (grown on demand)
+    uint32_t* d_pixels = nullptr;
+    int32_t* d_ids = nullptr;
+    size_t fb_capacity = 0, ids_capacity = 0;
+    int cached_seed = 0, cached_samples = -1;   // area-light offsets currently in h_offsets
+    std::string err;
+};
+
+struct softray_scene {
+    softray_ctx* ctx = nullptr;
+    DevScene dev;                      // passed to the kernel by value
+    std::vector<void*> allocs;         // every device allocation of this scene
+    std::vector<int32_t> mesh_tris;    // n_tris per mesh (hit-id bases)
+    uint64_t fingerprint = 1469598103934665603ull;
+    size_t device_bytes = 0;
+};
+
+static thread_local std::string g_last_error;
+
+static int fail(softray_ctx* ctx, int code, const std::string& msg)
+{
+    g_last_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+static int cuda_fail(softray_ctx* ctx, cudaError_t e, const char* what)
+{
+    const int code = (e == cudaErrorMemoryAllocation) ? SOFTRAY_E_OOM
+                     : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? SOFTRAY_E_NO_DEVICE
+                                                                                                                   : SOFTRAY_E_CUDA;
+    return fail(ctx, code, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+#define SR_CUDA(ctx, call)                                             \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) return cuda_fail((ctx), e__, #call);   \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// exact host math (Engine3D/Vector.cs, Matrix.cs) -- never contracted (see file header)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct hv { double x, y, z; };
+inline hv hmk(double x, double y, double z) { hv r = {x, y, z}; return r; }
+inline hv hsub(hv a, hv b) { return hmk(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline hv hscale(hv a, double s) { return hmk(a.x * s, a.y * s, a.z * s); }
+inline double hdot(hv a, hv b) { return a.x * b.x + a.y * b.y + a.z * b.z; }                 // Vector.cs:99-102
+inline hv hcross(hv a, hv b)                                                                   // Vector.cs:104-110
+{
+    return hmk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+inline hv hnormalise(hv a)                                                                     // Vector.cs:177-185
+{
+    const double inv = 1.0 / std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
+    return hscale(a, inv);
+}
+inline bool his_zero(hv a)                                                                     // Vector.cs:140-147
+{
+    const double e = 1e-10;
+    return -e < a.x && a.x < e && -e < a.y && a.y < e && -e < a.z && a.z < e;
+}
+inline hv hmul3x3(const double* m, hv v)                                                       // Matrix.cs:34-41
+{
+    return hmk(v.x * m[0] + v.y * m[1] + v.z * m[2], v.x * m[4] + v.y * m[5] + v.z * m[6],
+               v.x * m[8] + v.y * m[9] + v.z * m[10]);
+}
+inline hv hmul3x4(const double* m, hv v)                                                       // Matrix.cs:50-57
+{
+    return hmk(v.x * m[0] + v.y * m[1] + v.z * m[2] + m[3], v.x * m[4] + v.y * m[5] + v.z * m[6] + m[7],
+               v.x * m[8] + v.y * m[9] + v.z * m[10] + m[11]);
+}
+
+// 4x4 row-major product, accumulating from 0.0 over i = 0..3 (Matrix.cs:74-92)
+void mat_mul(const double* a, const double* b, double* out)
+{
+    double r[16];
+    for (int row = 0; row < 4; row++)
+        for (int col = 0; col < 4; col++) {
+            double sum = 0.0;
+            for (int i = 0; i < 4; i++) sum += a[row * 4 + i] * b[i * 4 + col];
+            r[row * 4 + col] = sum;
+        }
+    std::memcpy(out, r, sizeof r);
+}
+void mat_identity(double* m)
+{
+    std::memset(m, 0, 16 * sizeof(double));
+    m[0] = m[5] = m[10] = m[15] = 1.0;
+}
+void mat_translate(double* m, double x, double y, double z)   // Matrix.cs:94-114
+{
+    mat_identity(m);
+    m[3] = x; m[7] = y; m[11] = z;
+}
+void mat_yaw(double* m, double a)                             // Matrix.cs:116-132
+{
+    mat_identity(m);
+    m[0] = std::cos(a); m[8] = std::sin(a); m[2] = -std::sin(a); m[10] = std::cos(a);
+}
+void mat_pitch(double* m, double a)                           // Matrix.cs:134-150
+{
+    mat_identity(m);
+    m[5] = std::cos(a); m[9] = std::sin(a); m[6] = -std::sin(a); m[10] = std::cos(a);
+}
+void mat_roll(double* m, double a)                            // Matrix.cs:152-168
+{
+    mat_identity(m);
+    m[0] = std::cos(a); m[4] = std::sin(a); m[1] = -std::sin(a); m[5] = std::cos(a);
+}
+
+// System.Random(int seed) of the .NET Framework 4.x BCL (Knuth's subtractive generator; the
+// algorithm is not in the reference tree -- SURVEY.md Appendix B restates it).  ShadowMethod's
+// ctor draws the area-light offsets from it (ShadowMethod.cs:63-72, seeded at Renderer.cs:1624).
+class DotNetRandom {
+public:
+    explicit DotNetRandom(int32_t seed)
+    {
+        const int32_t kBig = 2147483647, kSeed = 161803398;
+        const int32_t sub = seed == INT32_MIN ? kBig : (seed < 0 ? -seed : seed);
+        int32_t mj = kSeed - sub, mk = 1;
+        std::memset(a_, 0, sizeof a_);
+        a_[55] = mj;
+        for (int i = 1; i < 55; i++) {
+            const int ii = (21 * i) % 55;
+            a_[ii] = mk;
+            mk = mj - mk;
+            if (mk < 0) mk += kBig;
+            mj = a_[ii];
+        }
+        for (int round = 0; round < 4; round++)
+            for (int i = 1; i < 56; i++) {
+                a_[i] = (int32_t)((uint32_t)a_[i] - (uint32_t)a_[1 + (i + 30) % 55]);
+                if (a_[i] < 0) a_[i] += kBig;
+            }
+        inext_ = 0; inextp_ = 21;
+    }
+    double next_double()
+    {
+        const int32_t kBig = 2147483647;
+        if (++inext_ >= 56) inext_ = 1;
+        if (++inextp_ >= 56) inextp_ = 1;
+        int32_t v = (int32_t)((uint32_t)a_[inext_] - (uint32_t)a_[inextp_]);
+        if (v == kBig) v--;
+        if (v < 0) v += kBig;
+        a_[inext_] = v;
+        return v * (1.0 / kBig);
+    }
+
+private:
+    int32_t a_[56];
+    int inext_, inextp_;
+};
+
+// offsets_i = normalise(2u-1, 2v-1, 2w-1) * 0.2 (ShadowMethod.cs:63-72, lightSourceRadius :10)
+void area_light_offsets(int32_t seed, int n, double* out)
+{
+    DotNetRandom rng(seed);
+    for (int i = 0; i < n; i++) {
+        const double a = rng.next_double() * 2 - 1;
+        const double b = rng.next_double() * 2 - 1;
+        const double c = rng.next_double() * 2 - 1;
+        const hv o = hscale(hnormalise(hmk(a, b, c)), 0.2);
+        out[3 * i] = o.x; out[3 * i + 1] = o.y; out[3 * i + 2] = o.z;
+    }
+}
+
+inline void fnv(uint64_t* h, const void* data, size_t n)
+{
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    uint64_t x = *h;
+    for (size_t i = 0; i < n; i++) { x ^= p[i]; x *= 1099511628211ull; }
+    *h = x;
+}
+
+// upload one host array; records the allocation and folds the bytes into the layout fingerprint
+template <typename T>
+int upload(softray_scene* sc, const std::vector<T>& host, const T** out)
+{
+    *out = nullptr;
+    if (host.empty()) return SOFTRAY_OK;
+    void* d = nullptr;
+    const size_t bytes = host.size() * sizeof(T);
+    SR_CUDA(sc->ctx, cudaMalloc(&d, bytes));
+    sc->allocs.push_back(d);
+    sc->device_bytes += bytes;
+    SR_CUDA(sc->ctx, cudaMemcpyAsync(d, host.data(), bytes, cudaMemcpyHostToDevice, sc->ctx->stream));
+    SR_CUDA(sc->ctx, cudaStreamSynchronize(sc->ctx->stream));
+    fnv(&sc->fingerprint, host.data(), bytes);
+    *out = static_cast<const T*>(d);
+    return SOFTRAY_OK;
+}
+
+// Triangle ctor + Plane ctor (Triangle.cs:29-57, Plane.cs:22-29) and the two denominators
+// Triangle.IntersectRay evaluates per call (Triangle.cs:90,95)
+void make_tri_rec(TriRec* t, hv v1, hv v2, hv v3, uint32_t color, int32_t index)
+{
+    const hv e1 = hsub(v2, v1), e2 = hsub(v3, v1);
+    hv n = hcross(e1, e2);
+    if (his_zero(n)) n = hmk(1, 0, 0);
+    const hv nn = hnormalise(n);
+    const hv e1p = hcross(e1, n), e2p = hcross(e2, n);
+    std::memset(t, 0, sizeof *t);
+    t->nx = nn.x; t->ny = nn.y; t->nz = nn.z;
+    t->d = hdot(v1, nn);
+    t->v1x = v1.x; t->v1y = v1.y; t->v1z = v1.z;
+    t->den1 = hdot(e1, e2p);
+    t->e2px = e2p.x; t->e2py = e2p.y; t->e2pz = e2p.z;
+    t->den2 = hdot(e2, e1p);
+    t->e1px = e1p.x; t->e1py = e1p.y; t->e1pz = e1p.z;
+    t->color = color;
+    t->index = index;
+}
+
+inline bool box_contains(const double* mn, const double* mx, hv p)   // AxisAlignedBox.cs:143-149
+{
+    const double e = 1e-10;
+    return mn[0] - e < p.x && p.x < mx[0] + e && mn[1] - e < p.y && p.y < mx[1] + e && mn[2] - e < p.z && p.z < mx[2] + e;
+}
+
+inline double max_abs3(const double* a, const double* b)
+{
+    double m = 0.0;
+    for (int k = 0; k < 3; k++) { m = std::fmax(m, std::fabs(a[k])); m = std::fmax(m, std::fabs(b[k])); }
+    return m;
+}
+
+// FP32 traversal slack (DESIGN.md "FP32 candidate search"): the slab test evaluates
+// fma(plane, 1/d, -o/d) with o, d and the box planes rounded to FP32; all those roundings together
+// move a box face by < 4e-7 * (largest coordinate in play).  Boxes are padded by 2^-18 of that
+// (~9.5x margin) so the test can only produce false positives.
+inline float traversal_pad(double max_coord) { return round_up(std::ldexp(std::fmax(max_coord, 1e-30), -18)); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int softray_abi_version(void) { return SOFTRAY_ABI_VERSION; }
+
+extern "C" int softray_abi_sizeof(int32_t which)
+{
+    switch (which) {
+    case 0: return (int)sizeof(softray_mesh);
+    case 1: return (int)sizeof(softray_sphere);
+    case 2: return (int)sizeof(softray_scene_desc);
+    case 3: return (int)sizeof(softray_instance);
+    case 4: return (int)sizeof(softray_frame);
+    case 5: return (int)sizeof(softray_stats);
+    default: return -1;
+    }
+}
+
+extern "C" const char* softray_last_error(const softray_ctx* ctx)
+{
+    return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+extern "C" void softray_destroy(softray_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_insts); cudaFree(ctx->d_offsets); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_pixels); cudaFree(ctx->d_ids);
+    cudaFreeHost(ctx->h_insts); cudaFreeHost(ctx->h_offsets); cudaFreeHost(ctx->h_counters);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int softray_create(int32_t device_ordinal, softray_ctx** out)
+{
+    if (!out) return fail(nullptr, SOFTRAY_E_INVALID_ARG, "softray_create: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, SOFTRAY_E_NO_DEVICE,
+                    std::string("softray_create: no CUDA device (there is no CPU fallback)") +
+                        (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : std::string()));
+    if (device_ordinal < 0 || device_ordinal >= n_dev)
+        return fail(nullptr, SOFTRAY_E_INVALID_ARG, "softray_create: device ordinal out of range");
+    softray_ctx* ctx = new (std::nothrow) softray_ctx();
+    if (!ctx) return fail(nullptr, SOFTRAY_E_OOM, "softray_create: out of host memory");
+    ctx->device = device_ordinal;
+    int rc = [&]() -> int {
+        SR_CUDA(ctx, cudaSetDevice(device_ordinal));
+        SR_CUDA(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal));
+        SR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        for (auto& ev : ctx->ev) SR_CUDA(ctx, cudaEventCreate(&ev));
+        SR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming));
+        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_insts, sizeof(DevInstance) * SOFTRAY_MAX_INSTANCES));
+        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_offsets, sizeof(double) * 3 * SOFTRAY_MAX_SHADOW_SAMPLES));
+        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_tile_counter, sizeof(unsigned int)));
+        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_counters, sizeof(DevCounters)));
+        SR_CUDA(ctx, cudaMallocHost((void**)&ctx->h_insts, sizeof(DevInstance) * SOFTRAY_MAX_INSTANCES));
+        SR_CUDA(ctx, cudaMallocHost((void**)&ctx->h_offsets, sizeof(double) * 3 * SOFTRAY_MAX_SHADOW_SAMPLES));
+        SR_CUDA(ctx, cudaMallocHost((void**)&ctx->h_counters, sizeof(DevCounters)));
+        return SOFTRAY_OK;
+    }();
+    if (rc != SOFTRAY_OK) {
+        g_last_error = ctx->err;
+        softray_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return SOFTRAY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene
+// ---------------------------------------------------------------------------------------------
+extern "C" void softray_scene_destroy(softray_scene* scene)
+{
+    if (!scene) return;
+    if (scene->ctx) {
+        cudaSetDevice(scene->ctx->device);
+        cudaStreamSynchronize(scene->ctx->stream);
+    }
+    for (void* p : scene->allocs) cudaFree(p);
+    delete scene;
+}
+
+static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
+{
+    softray_ctx* ctx = sc->ctx;
+    const bool brute = desc->accel == SOFTRAY_ACCEL_BRUTE;
+    std::vector<DevMesh> meshes((size_t)desc->n_meshes);
+    for (int32_t mi = 0; mi < desc->n_meshes; mi++) {
+        const softray_mesh& m = desc->meshes[mi];
+        if (m.n_tris < 0 || m.n_verts < 0 || (m.n_tris > 0 && (!m.verts_xyz || !m.tri_vidx || !m.tri_argb)))
+            return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: mesh arrays missing");
+        std::vector<TriRec> recs((size_t)m.n_tris);
+        std::vector<PrimBounds> bounds((size_t)m.n_tris);
+        for (int32_t i = 0; i < m.n_tris; i++) {
+            hv v[3];
+            for (int k = 0; k < 3; k++) {
+                const int32_t vi = m.tri_vidx[3 * (size_t)i + k];
+                if (vi < 0 || vi >= m.n_verts) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: vertex index out of range");
+                v[k] = hmk(m.verts_xyz[3 * (size_t)vi], m.verts_xyz[3 * (size_t)vi + 1], m.verts_xyz[3 * (size_t)vi + 2]);
+                // SpatialSubdivision ctor: every vertex inside the bounding box (SpatialSubdivision.cs:285-295)
+                if (!box_contains(m.bbox_min, m.bbox_max, v[k]))
+                    return fail(ctx, SOFTRAY_E_VERTEX_OUTSIDE_BBOX, "A triangle vertex is outside the bounding box");
+            }
+            make_tri_rec(&recs[(size_t)i], v[0], v[1], v[2], m.tri_argb[i], i);
+            PrimBounds& b = bounds[(size_t)i];
+            const double xs[3] = {v[0].x, v[1].x, v[2].x}, ys[3] = {v[0].y, v[1].y, v[2].y}, zs[3] = {v[0].z, v[1].z, v[2].z};
+            b.lo[0] = round_down(std::fmin(xs[0], std::fmin(xs[1], xs[2]))); b.hi[0] = round_up(std::fmax(xs[0], std::fmax(xs[1], xs[2])));
+            b.lo[1] = round_down(std::fmin(ys[0], std::fmin(ys[1], ys[2]))); b.hi[1] = round_up(std::fmax(ys[0], std::fmax(ys[1], ys[2])));
+            b.lo[2] = round_down(std::fmin(zs[0], std::fmin(zs[1], zs[2]))); b.hi[2] = round_up(std::fmax(zs[0], std::fmax(zs[1], zs[2])));
+        }
+        DevMesh& dm = meshes[(size_t)mi];
+        std::memset(&dm, 0, sizeof dm);
+        dm.n_tris = m.n_tris;
+        for (int k = 0; k < 3; k++) { dm.bmin[k] = m.bbox_min[k]; dm.bmax[k] = m.bbox_max[k]; }
+        sc->mesh_tris.push_back(m.n_tris);
+        if (m.n_tris == 0) continue;
+        if (brute) {
+            int rc = upload(sc, recs, &dm.tris);
+            if (rc != SOFTRAY_OK) return rc;
+        } else {
+            BvhBuild bvh;
+            build_bvh(bounds, traversal_pad(max_abs3(m.bbox_min, m.bbox_max)), kMaxLeafPrims, &bvh);
+            if (bvh.depth >= kStackEntries) return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_scene_create: BVH too deep");
+            std::vector<TriRec> ordered((size_t)m.n_tris);
+            for (int32_t k = 0; k < m.n_tris; k++) ordered[(size_t)k] = recs[(size_t)bvh.order[(size_t)k]];
+            int rc = upload(sc, ordered, &dm.tris);
+            if (rc != SOFTRAY_OK) return rc;
+            rc = upload(sc, bvh.nodes, &dm.nodes);
+            if (rc != SOFTRAY_OK) return rc;
+            dm.n_nodes = (int32_t)bvh.nodes.size();
+        }
+    }
+
+    DevScene& ds = sc->dev;
+    std::memset(&ds, 0, sizeof ds);
+    ds.n_meshes = desc->n_meshes;
+    ds.accel = desc->accel;
+    ds.n_spheres = desc->n_spheres;
+    if (desc->n_spheres > 0) {
+        std::vector<SphereRec> recs((size_t)desc->n_spheres);
+        std::vector<PrimBounds> bounds((size_t)desc->n_spheres);
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int32_t i = 0; i < desc->n_spheres; i++) {
+            const softray_sphere& s = desc->spheres[i];
+            if (!(s.r >= 0.0) || !std::isfinite(s.cx) || !std::isfinite(s.cy) || !std::isfinite(s.cz) || !std::isfinite(s.r))
+                return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: sphere is not finite");
+            SphereRec& r = recs[(size_t)i];
+            std::memset(&r, 0, sizeof r);
+            r.cx = s.cx; r.cy = s.cy; r.cz = s.cz; r.r = s.r;
+            r.r2 = s.r * s.r;                                   // Sphere.cs:30
+            r.color = s.argb; r.index = i;
+            const double c[3] = {s.cx, s.cy, s.cz};
+            for (int k = 0; k < 3; k++) {
+                bounds[(size_t)i].lo[k] = round_down(c[k] - s.r);
+                bounds[(size_t)i].hi[k] = round_up(c[k] + s.r);
+                lo[k] = std::fmin(lo[k], c[k] - s.r); hi[k] = std::fmax(hi[k], c[k] + s.r);
+            }
+        }
+        for (int k = 0; k < 3; k++) { ds.sph_bmin[k] = lo[k]; ds.sph_bmax[k] = hi[k]; }
+        if (brute) {
+            int rc = upload(sc, recs, &ds.spheres);
+            if (rc != SOFTRAY_OK) return rc;
+        } else {
+            BvhBuild bvh;
+            const float pad = traversal_pad(max_abs3(lo, hi));
+            build_bvh(bounds, pad, kMaxLeafPrims, &bvh);
+            if (bvh.depth >= kStackEntries) return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_scene_create: BVH too deep");
+            std::vector<SphereRec> ordered((size_t)desc->n_spheres);
+            for (int32_t k = 0; k < desc->n_spheres; k++) ordered[(size_t)k] = recs[(size_t)bvh.order[(size_t)k]];
+            int rc = upload(sc, ordered, &ds.spheres);
+            if (rc != SOFTRAY_OK) return rc;
+            rc = upload(sc, bvh.nodes, &ds.sphere_nodes);
+            if (rc != SOFTRAY_OK) return rc;
+            ds.n_sphere_nodes = (int32_t)bvh.nodes.size();
+            // the entry clip works on the padded bounds
+            for (int k = 0; k < 3; k++) { ds.sph_bmin[k] = lo[k] - (double)pad; ds.sph_bmax[k] = hi[k] + (double)pad; }
+        }
+    }
+    if (!meshes.empty()) {
+        // the DevMesh table itself holds device pointers: fold only its layout-relevant fields
+        for (const DevMesh& dm : meshes) {
+            fnv(&sc->fingerprint, &dm.n_tris, sizeof dm.n_tris);
+            fnv(&sc->fingerprint, &dm.n_nodes, sizeof dm.n_nodes);
+            fnv(&sc->fingerprint, dm.bmin, sizeof dm.bmin);
+            fnv(&sc->fingerprint, dm.bmax, sizeof dm.bmax);
+        }
+        const uint64_t keep = sc->fingerprint;
+        int rc = upload(sc, meshes, &ds.meshes);
+        sc->fingerprint = keep;
+        if (rc != SOFTRAY_OK) return rc;
+    }
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_scene_create(softray_ctx* ctx, const softray_scene_desc* desc, softray_scene** out)
+{
+    if (!ctx || !desc || !out) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: NULL argument");
+    *out = nullptr;
+    if (desc->n_meshes < 0 || desc->n_spheres < 0 || (desc->n_meshes > 0 && !desc->meshes) ||
+        (desc->n_spheres > 0 && !desc->spheres))
+        return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: bad counts or NULL arrays");
+    if (desc->accel != SOFTRAY_ACCEL_BVH && desc->accel != SOFTRAY_ACCEL_BRUTE)
+        return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: unknown accel");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    softray_scene* sc = new (std::nothrow) softray_scene();
+    if (!sc) return fail(ctx, SOFTRAY_E_OOM, "softray_scene_create: out of host memory");
+    sc->ctx = ctx;
+    int rc;
+    try {
+        rc = build_scene(sc, desc);
+    } catch (const std::bad_alloc&) {
+        rc = fail(ctx, SOFTRAY_E_OOM, "softray_scene_create: out of host memory");
+    }
+    if (rc != SOFTRAY_OK) {
+        softray_scene_destroy(sc);
+        return rc;
+    }
+    *out = sc;
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_scene_fingerprint(const softray_scene* scene, uint64_t* out)
+{
+    if (!scene || !out) return fail(nullptr, SOFTRAY_E_INVALID_ARG, "softray_scene_fingerprint: NULL argument");
+    *out = scene->fingerprint;
+    return SOFTRAY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Prepared {
+    DevFrame f;
+    int grid = 0;
+    size_t smem = 0;
+    int start_row = 0, end_row = -1;
+};
+
+int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_frame* fr, Prepared* p)
+{
+    if (!fr->instances) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: frame.instances is NULL");
+    if (fr->width <= 0 || fr->height <= 0 || fr->sub_pixel_res < 1 || fr->n_instances < 1 ||
+        fr->n_instances > SOFTRAY_MAX_INSTANCES)
+        return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: bad surface size, sub_pixel_res or instance count");
+    if (fr->shadows && (fr->shadow_samples < 1 || fr->shadow_samples > SOFTRAY_MAX_SHADOW_SAMPLES))
+        return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: shadow_samples out of range");
+    if (fr->reflection_depth < 0 || fr->reflection_depth > 4)
+        return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: reflection_depth out of range");
+    if (fr->band_count > 1 && (fr->band_index < 0 || fr->band_index >= fr->band_count))
+        return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: band_index out of range");
+    if (fr->texture3d_id != 0 && fr->texture3d_id != 1)
+        return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: unknown texture3d_id");
+    if (fr->n_instances > 1 && (scene->dev.n_spheres > 0 || fr->shadows || (fr->focal_blur && fr->sub_pixel_res > 1) ||
+                                fr->reflection_depth))
+        return fail(ctx, SOFTRAY_E_UNSUPPORTED,
+                    "softray_render: composite (multi-instance) frames support primary rays + shading only");
+
+    if (ctx->staging_busy) {   // an asynchronous earlier frame may still be reading h_insts / h_offsets
+        SR_CUDA(ctx, cudaEventSynchronize(ctx->ev_staged));
+        ctx->staging_busy = false;
+    }
+    DevFrame& f = p->f;
+    std::memset(&f, 0, sizeof f);
+    f.ambient = fr->ambient; f.shininess = fr->shininess;
+    for (int k = 0; k < 3; k++) { f.light_dir_view[k] = fr->light_dir_view[k]; f.light_pos_view[k] = fr->light_pos_view[k]; }
+    f.fov_depth = fr->fov_depth; f.focal_depth = fr->focal_depth; f.focal_strength = fr->focal_strength;
+    f.aspect = (double)fr->height / (double)fr->width;                 // Renderer.cs:621
+    f.width = fr->width; f.height = fr->height;
+    // clamp rows like Renderer.cs:1652-1653
+    int s = fr->start_row < 0 ? 0 : fr->start_row; if (s > fr->height - 1) s = fr->height - 1;
+    int e = fr->end_row < 0 ? 0 : fr->end_row;     if (e > fr->height - 1) e = fr->height - 1;
+    f.start_row = s; f.end_row = e;
+    p->start_row = s; p->end_row = e;
+    f.sub_pixel_res = fr->sub_pixel_res;
+    f.focal_blur = fr->focal_blur ? 1 : 0;
+    f.subdivision = fr->subdivision ? 1 : 0;
+    f.shading = fr->shading ? 1 : 0;
+    f.shadows = fr->shadows ? 1 : 0;
+    f.shadow_samples = fr->shadows ? fr->shadow_samples : 0;
+    f.point_lighting = fr->point_lighting ? 1 : 0;
+    f.specular_lighting = fr->specular_lighting ? 1 : 0;
+    f.reflection_depth = fr->reflection_depth;
+    f.texture3d_id = fr->texture3d_id;
+    f.n_instances = fr->n_instances;
+    f.background = fr->background_argb | 0xFF000000u;                  // Renderer.cs:325-331,1860
+    const int rows = e - s + 1;
+    const bool banded = fr->band_count > 1 && fr->band_height > 0;
+    f.band_height = banded ? fr->band_height : rows;
+    f.band_count = banded ? fr->band_count : 1;
+    f.band_index = banded ? fr->band_index : 0;
+
+    int32_t base = 0;
+    for (int32_t i = 0; i < fr->n_instances; i++) {
+        const softray_instance& in = fr->instances[i];
+        if (in.mesh_id < 0 || in.mesh_id >= scene->dev.n_meshes)
+            return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: instance.mesh_id out of range");
+        DevInstance& d = ctx->h_insts[i];
+        std::memset(&d, 0, sizeof d);
+        std::memcpy(d.M, in.M, sizeof d.M);            // rows 0..2
+        std::memcpy(d.Minv, in.Minv, sizeof d.Minv);
+        d.pos_z = in.pos[2];
+        // start_World = TransformDirectionReverse((0,0,-Position.z)) (Renderer.cs:1717); composite
+        // frames use the full inverse transform of the view origin
+        const hv st = fr->n_instances == 1 ? hmul3x3(in.Minv, hmk(0, 0, -in.pos[2])) : hmul3x4(in.Minv, hmk(0, 0, 0));
+        d.start[0] = st.x; d.start[1] = st.y; d.start[2] = st.z;
+        // Renderer.cs:1513-1515 with Instance.TransformPosFromView = Minv * pos (Instance.cs:203)
+        const hv ld = hmul3x3(in.Minv, hmk(fr->light_dir_view[0], fr->light_dir_view[1], fr->light_dir_view[2]));
+        const hv lp = hmul3x4(in.Minv, hmk(fr->light_pos_view[0], fr->light_pos_view[1], fr->light_pos_view[2]));
+        d.light_dir_model[0] = ld.x; d.light_dir_model[1] = ld.y; d.light_dir_model[2] = ld.z;
+        d.light_pos_model[0] = lp.x; d.light_pos_model[1] = lp.y; d.light_pos_model[2] = lp.z;
+        d.mesh = in.mesh_id;
+        d.tri_base = base;
+        base += scene->mesh_tris[(size_t)in.mesh_id];
+    }
+    if (f.shadows && (ctx->cached_samples != f.shadow_samples || ctx->cached_seed != fr->random_seed)) {
+        area_light_offsets(fr->random_seed, f.shadow_samples, ctx->h_offsets);
+        ctx->cached_samples = f.shadow_samples; ctx->cached_seed = fr->random_seed;
+    }
+
+    // one warp per 8x4-pixel tile, pulled from an atomic queue by persistent warps
+    const int n_bands = (rows + f.band_height - 1) / f.band_height;
+    const int my_bands = f.band_index < n_bands ? (n_bands - f.band_index + f.band_count - 1) / f.band_count : 0;
+    f.tiles_x = (f.width + 7) / 8;
+    f.tiles_per_band = (f.band_height + 3) / 4;
+    f.tiles_y = my_bands * f.tiles_per_band;
+    p->smem = sizeof(DevInstance) * (size_t)f.n_instances + sizeof(double) * 3 * (size_t)f.shadow_samples;
+    int occ = render_kernel_occupancy((int)p->smem);
+    if (occ < 1) occ = 1;
+    const long long n_tiles = (long long)f.tiles_x * f.tiles_y;
+    long long grid = (long long)ctx->sm_count * occ;
+    const long long need = (n_tiles + 3) / 4;            // 4 warps per block
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    p->grid = (int)grid;
+    return SOFTRAY_OK;
+}
+
+int enqueue_frame(softray_ctx* ctx, const softray_scene* scene, const Prepared& p, uint32_t* d_pixels, int32_t* d_ids,
+                  cudaStream_t stream, bool timed)
+{
+    const DevFrame& f = p.f;
+    if (timed) SR_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
+    SR_CUDA(ctx, cudaMemcpyAsync(ctx->d_insts, ctx->h_insts, sizeof(DevInstance) * (size_t)f.n_instances,
+                                 cudaMemcpyHostToDevice, stream));
+    if (f.shadows)
+        SR_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, ctx->h_offsets, sizeof(double) * 3 * (size_t)f.shadow_samples,
+                                     cudaMemcpyHostToDevice, stream));
+    SR_CUDA(ctx, cudaEventRecord(ctx->ev_staged, stream));
+    ctx->staging_busy = true;
+    SR_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned int), stream));
+    SR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DevCounters), stream));
+    if (timed) SR_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
+    SR_CUDA(ctx, launch_render(f, scene->dev, ctx->d_insts, ctx->d_offsets, d_pixels, d_ids, ctx->d_tile_counter,
+                               ctx->d_counters, p.grid, stream));
+    if (timed) SR_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
+    return SOFTRAY_OK;
+}
+
+int collect_stats(softray_ctx* ctx, cudaStream_t stream, softray_stats* st, bool have_d2h_event)
+{
+    SR_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, stream));
+    SR_CUDA(ctx, cudaStreamSynchronize(stream));
+    std::memset(st, 0, sizeof *st);
+    const DevCounters& c = *ctx->h_counters;
+    st->rays_primary = c.rays_primary; st->rays_shadow = c.rays_shadow; st->rays_secondary = c.rays_secondary;
+    st->node_visits = c.node_visits; st->prim_tests = c.prim_tests; st->sphere_tests = c.sphere_tests;
+    st->hits_primary = c.hits_primary; st->shaded_hits = c.shaded_hits;
+    st->launches = 1;
+    float ms = 0.f;
+    SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); st->ms_h2d = ms;
+    SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); st->ms_kernel = ms;
+    if (have_d2h_event) { SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); st->ms_d2h = ms; }
+    return SOFTRAY_OK;
+}
+
+}  // namespace
+
+extern "C" int softray_render_device(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
+                                     uint32_t* d_pixels_argb, int32_t* d_hit_ids, void* stream, softray_stats* stats)
+{
+    if (!ctx || !scene || !frame || !d_pixels_argb) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render_device: NULL argument");
+    if (scene->ctx != ctx) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render_device: scene belongs to another context");
+    const auto t0 = std::chrono::steady_clock::now();
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    Prepared p;
+    int rc = prepare_frame(ctx, scene, frame, &p);
+    if (rc != SOFTRAY_OK) return rc;
+    if (p.f.tiles_y == 0) return SOFTRAY_OK;
+    rc = enqueue_frame(ctx, scene, p, d_pixels_argb, d_hit_ids, s, stats != nullptr);
+    if (rc != SOFTRAY_OK) return rc;
+    if (stats) {
+        rc = collect_stats(ctx, s, stats, false);
+        if (rc != SOFTRAY_OK) return rc;
+        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_render(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
+                              uint32_t* pixels_argb, int32_t* hit_ids, softray_stats* stats)
+{
+    if (!ctx || !scene || !frame || !pixels_argb) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: NULL argument");
+    if (scene->ctx != ctx) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: scene belongs to another context");
+    const auto t0 = std::chrono::steady_clock::now();
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    Prepared p;
+    int rc = prepare_frame(ctx, scene, frame, &p);
+    if (rc != SOFTRAY_OK) return rc;
+    const size_t n_px = (size_t)frame->width * (size_t)frame->height;
+    if (ctx->fb_capacity < n_px) {
+        cudaFree(ctx->d_pixels); ctx->d_pixels = nullptr; ctx->fb_capacity = 0;
+        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_pixels, n_px * sizeof(uint32_t)));
+        ctx->fb_capacity = n_px;
+    }
+    if (hit_ids && ctx->ids_capacity < n_px) {
+        cudaFree(ctx->d_ids); ctx->d_ids = nullptr; ctx->ids_capacity = 0;
+        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_ids, n_px * sizeof(int32_t)));
+        ctx->ids_capacity = n_px;
+    }
+    cudaStream_t s = ctx->stream;
+    rc = enqueue_frame(ctx, scene, p, ctx->d_pixels, hit_ids ? ctx->d_ids : nullptr, s, true);
+    if (rc != SOFTRAY_OK) return rc;
+    // read back exactly the rows that were rendered; banded frames copy each
+    // band of this rank separately so the caller's other rows stay untouched
+    const size_t W = (size_t)frame->width;
+    const bool banded = p.f.band_count > 1;
+    const int bh = banded ? p.f.band_height : (p.end_row - p.start_row + 1);
+    for (int top = p.start_row, b = 0; top <= p.end_row; top += bh, b++) {
+        if (banded && b % p.f.band_count != p.f.band_index) continue;
+        const int last = top + bh - 1 > p.end_row ? p.end_row : top + bh - 1;
+        const size_t off = (size_t)top * W, cnt = (size_t)(last - top + 1) * W;
+        SR_CUDA(ctx, cudaMemcpyAsync(pixels_argb + off, ctx->d_pixels + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (hit_ids)
+            SR_CUDA(ctx, cudaMemcpyAsync(hit_ids + off, ctx->d_ids + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    SR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+    if (stats) {
+        rc = collect_stats(ctx, s, stats, true);
+        if (rc != SOFTRAY_OK) return rc;
+        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    } else {
+        SR_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return SOFTRAY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU: peer-mapped framebuffer
+// ---------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == SOFTRAY_IPC_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int softray_device_alloc(softray_ctx* ctx, uint64_t bytes, void** d_ptr_out)
+{
+    if (!ctx || !d_ptr_out || bytes == 0) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_device_alloc: bad argument");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    SR_CUDA(ctx, cudaMalloc(d_ptr_out, (size_t)bytes));
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_device_free(softray_ctx* ctx, void* d_ptr)
+{
+    if (!ctx) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_device_free: NULL context");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    SR_CUDA(ctx, cudaFree(d_ptr));
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_ipc_export(softray_ctx* ctx, void* d_ptr, char handle[SOFTRAY_IPC_HANDLE_BYTES])
+{
+    if (!ctx || !d_ptr || !handle) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_ipc_export: NULL argument");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    SR_CUDA(ctx, cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle, &h, sizeof h);
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_ipc_open(softray_ctx* ctx, const char handle[SOFTRAY_IPC_HANDLE_BYTES], void** d_ptr_out)
+{
+    if (!ctx || !handle || !d_ptr_out) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_ipc_open: NULL argument");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    SR_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_ipc_close(softray_ctx* ctx, void* d_ptr)
+{
+    if (!ctx || !d_ptr) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_ipc_close: NULL argument");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    SR_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return SOFTRAY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------------------------
+extern "C" int softray_measure_fma_peak(softray_ctx* ctx, int32_t fp64, double* tflops_out)
+{
+    if (!ctx || !tflops_out) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_measure_fma_peak: NULL argument");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    SR_CUDA(ctx, measure_fma_peak(fp64 != 0, ctx->sm_count, ctx->stream, tflops_out));
+    return SOFTRAY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers mirroring small reference functions
+// ---------------------------------------------------------------------------------------------
+extern "C" void softray_instance_init(softray_instance* inst, const double pos[3], double yaw, double pitch, double roll,
+                                      int32_t mesh_id)
+{
+    if (!inst || !pos) return;
+    // _transform = T(pos) * Roll * Pitch * Yaw; _inverseTransform = Yaw(-) * Pitch(-) * Roll(-) * T(-pos)
+    // (Instance.cs:134-135)
+    double t[16], r[16], p[16], y[16], a[16], b[16];
+    mat_translate(t, pos[0], pos[1], pos[2]); mat_roll(r, roll); mat_pitch(p, pitch); mat_yaw(y, yaw);
+    mat_mul(t, r, a); mat_mul(a, p, b); mat_mul(b, y, inst->M);
+    mat_yaw(y, -yaw); mat_pitch(p, -pitch); mat_roll(r, -roll); mat_translate(t, -pos[0], -pos[1], -pos[2]);
+    mat_mul(y, p, a); mat_mul(a, r, b); mat_mul(b, t, inst->Minv);
+    inst->pos[0] = pos[0]; inst->pos[1] = pos[1]; inst->pos[2] = pos[2];
+    inst->mesh_id = mesh_id;
+    inst->_pad = 0;
+}
+
+extern "C" void softray_frame_defaults(softray_frame* f, int32_t width, int32_t height)
+{
+    if (!f) return;
+    std::memset(f, 0, sizeof *f);
+    f->ambient = 0.1;                                                // Renderer.cs:207-217
+    const hv d = hnormalise(hmk(-1, -1, 1));
+    f->light_dir_view[0] = d.x; f->light_dir_view[1] = d.y; f->light_dir_view[2] = d.z;
+    const hv lp = hsub(hmk(0.0, 0.0, 1.5), hscale(d, 2));
+    f->light_pos_view[0] = lp.x; f->light_pos_view[1] = lp.y; f->light_pos_view[2] = lp.z;
+    f->shininess = 100.0;
+    const double fov_rad = 45.0 / 180.0 * 3.14159265358979323846;    // Renderer.cs:97-101
+    f->fov_depth = 0.5 / std::tan(fov_rad / 2);
+    f->focal_depth = 1.5; f->focal_strength = 10.0;                  // Renderer.cs:79-83
+    f->width = width; f->height = height;
+    f->start_row = 0; f->end_row = height - 1;
+    f->sub_pixel_res = 1; f->focal_blur = 1; f->subdivision = 1; f->shading = 1; f->shadows = 0;
+    f->shadow_samples = 100;                                         // ShadowMethod.cs:9
+    f->point_lighting = 1; f->specular_lighting = 1;
+    f->random_seed = 1234567890;                                     // Renderer.cs:85
+    f->band_height = 0; f->band_count = 1; f->band_index = 0;
+}

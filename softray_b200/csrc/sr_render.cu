@@ -1,0 +1,706 @@
+// sr_render.cu -- the fused raytrace kernel for sm_100a: ray generation, BVH traversal,
+// ray/sphere + ray/triangle intersection, Lambert/Phong shading, soft shadow rays, bounded
+// reflection, Texture3D modulation, sub-pixel accumulation and the packed-ARGB store, in one
+// persistent launch.  Replaces RaytraceBlock -> TraceRayComplex -> IRayIntersectable.IntersectRay
+// -> Surface.DrawPixel (Engine3D/Renderer.cs:1690-1925 and the Raytrace/*Method.cs decorators).
+//
+// Numerics.  Every decision the reference takes in FP64 (which primitive wins, rayFrac, position,
+// normal, lighting, truncation to bytes) is taken here with the SAME operations in the SAME order,
+// written with __dmul_rn/__dadd_rn/... so nvcc can never contract them into FMAs (the reference
+// never fuses).  Only the search for candidates is approximate: BVH boxes are
+// FP32, rounded outward and padded, so the slab test can only produce false positives.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "sr_types.h"
+
+namespace sr {
+
+// ---------------------------------------------------------------------------------------------
+// exact FP64 vector helpers (no contraction, left-to-right like Engine3D/Vector.cs)
+// ---------------------------------------------------------------------------------------------
+struct d3 { double x, y, z; };
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ d3 mk(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ d3 vadd(d3 a, d3 b) { return mk(dadd(a.x, b.x), dadd(a.y, b.y), dadd(a.z, b.z)); }
+__device__ __forceinline__ d3 vsub(d3 a, d3 b) { return mk(dsub(a.x, b.x), dsub(a.y, b.y), dsub(a.z, b.z)); }
+__device__ __forceinline__ d3 vscale(d3 a, double s) { return mk(dmul(a.x, s), dmul(a.y, s), dmul(a.z, s)); }
+__device__ __forceinline__ d3 vneg(d3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ double vdot(d3 a, d3 b)
+{
+    return dadd(dadd(dmul(a.x, b.x), dmul(a.y, b.y)), dmul(a.z, b.z));   // Vector.cs:99-102
+}
+__device__ __forceinline__ double vlen(d3 a) { return __dsqrt_rn(vdot(a, a)); }   // Vector.cs:121-128
+__device__ __forceinline__ d3 vnormalise(d3 a)                                    // Vector.cs:177-185
+{
+    double inv = ddiv(1.0, vlen(a));
+    return vscale(a, inv);
+}
+// Matrix.Multiply3X3 / TransformDirection[Reverse] on a 3x4 row-major block (Matrix.cs:34-41)
+__device__ __forceinline__ d3 mul3x3(const double* m, d3 v)
+{
+    return mk(dadd(dadd(dmul(v.x, m[0]), dmul(v.y, m[1])), dmul(v.z, m[2])),
+              dadd(dadd(dmul(v.x, m[4]), dmul(v.y, m[5])), dmul(v.z, m[6])),
+              dadd(dadd(dmul(v.x, m[8]), dmul(v.y, m[9])), dmul(v.z, m[10])));
+}
+// Matrix.Multiply3X4 (Matrix.cs:50-57)
+__device__ __forceinline__ d3 mul3x4(const double* m, d3 v)
+{
+    return mk(dadd(dadd(dadd(dmul(v.x, m[0]), dmul(v.y, m[1])), dmul(v.z, m[2])), m[3]),
+              dadd(dadd(dadd(dmul(v.x, m[4]), dmul(v.y, m[5])), dmul(v.z, m[6])), m[7]),
+              dadd(dadd(dadd(dmul(v.x, m[8]), dmul(v.y, m[9])), dmul(v.z, m[10])), m[11]));
+}
+
+// Color.ModulatePackedColor (Color.cs:124-133)
+__device__ __forceinline__ uint32_t modulate(uint32_t c, uint32_t amount)
+{
+    uint32_t r = (((c >> 16) & 0xff) * amount) >> 8;
+    uint32_t g = (((c >> 8) & 0xff) * amount) >> 8;
+    uint32_t b = ((c & 0xff) * amount) >> 8;
+    return 0xff000000u | (r << 16) | (g << 8) | b;
+}
+// C# (byte)double for an in-range value: truncation
+__device__ __forceinline__ uint32_t to_byte(double v) { return (uint32_t)__double2int_rz(v) & 0xffu; }
+
+// Texture3D extension, id 1: Texture3DCache index quantisation (Texture3DCache.cs:98-100)
+// with N = 128, clamped, then an integer pattern.
+__device__ __forceinline__ uint32_t texture3d_sample(int id, d3 p)
+{
+    if (id != 1) return 255u;
+    const double n1 = 127.0;
+    int qx = __double2int_rz(dmul(dadd(p.x, 0.5), n1));
+    int qy = __double2int_rz(dmul(dadd(p.y, 0.5), n1));
+    int qz = __double2int_rz(dmul(dadd(p.z, 0.5), n1));
+    qx = min(max(qx, 0), 127); qy = min(max(qy, 0), 127); qz = min(max(qz, 0), 127);
+    int cell = ((qx >> 3) ^ (qy >> 3) ^ (qz >> 3)) & 1;
+    int grain = (qx * 3 + qy * 5 + qz * 7) & 31;
+    return (uint32_t)(255 - cell * 80 - grain);
+}
+__device__ __forceinline__ uint32_t mirror_blend(uint32_t local, uint32_t refl)
+{
+    uint32_t r = (3u * ((local >> 16) & 0xff) + ((refl >> 16) & 0xff)) >> 2;
+    uint32_t g = (3u * ((local >> 8) & 0xff) + ((refl >> 8) & 0xff)) >> 2;
+    uint32_t b = (3u * (local & 0xff) + (refl & 0xff)) >> 2;
+    return 0xff000000u | (r << 16) | (g << 8) | b;
+}
+
+struct Counters { unsigned int node_visits, prim_tests, sphere_tests, shaded; };
+
+// ---------------------------------------------------------------------------------------------
+// exact primitive tests
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldg2(const void* p, int i)
+{
+    return __ldg(reinterpret_cast<const double2*>(p) + i);
+}
+
+// Triangle.IntersectRay + Plane.IntersectRay (Triangle.cs:83-104, Plane.cs:67-103).
+// `limit`: hits with rayFrac > limit are of no use to the caller (they lose the strict `<`).
+__device__ __forceinline__ bool tri_intersect(const TriRec* __restrict__ t, d3 s, d3 dir, double limit, double* rf_out)
+{
+    const double2 a0 = ldg2(t, 0), a1 = ldg2(t, 1);          // n.x n.y | n.z d
+    const d3 n = mk(a0.x, a0.y, a1.x);
+    const double start_dist = vdot(s, n);
+    const double dir_dist = vdot(dir, n);
+    if (dir_dist >= 0.0) return false;                        // one-sided
+    double rf = dsub(a1.y, start_dist);
+    if (!(rf <= 0.0)) return false;
+    rf = ddiv(rf, dir_dist);
+    if (rf > limit) return false;
+    const d3 pos = vadd(s, vscale(dir, rf));
+    const double2 a2 = ldg2(t, 2), a3 = ldg2(t, 3);          // v1.x v1.y | v1.z den1
+    const d3 w = vsub(pos, mk(a2.x, a2.y, a3.x));
+    const double2 a4 = ldg2(t, 4), a5 = ldg2(t, 5);          // e2p.x e2p.y | e2p.z den2
+    const double sN = ddiv(vdot(w, mk(a4.x, a4.y, a5.x)), a3.y);
+    if (sN < 0.0 || sN > 1.0) return false;
+    const double2 a6 = ldg2(t, 6), a7 = ldg2(t, 7);          // e1p.x e1p.y | e1p.z (color,index)
+    const double u = ddiv(vdot(w, mk(a6.x, a6.y, a7.x)), a5.y);
+    if (sN >= 0.0 && u >= 0.0 && dadd(sN, u) <= 1.0) { *rf_out = rf; return true; }
+    return false;
+}
+
+// Sphere.IntersectRay up to rayFrac (Sphere.cs:152-192); dirn = dir after Vector.Normalise.
+__device__ __forceinline__ bool sphere_intersect(const SphereRec* __restrict__ sp, d3 s, d3 dirn, double* rf_out)
+{
+    const double2 a0 = ldg2(sp, 0), a1 = ldg2(sp, 1), a2 = ldg2(sp, 2);   // c.x c.y | c.z r | r2 (color,index)
+    const d3 o = vsub(s, mk(a0.x, a0.y, a1.x));
+    const double proj = vdot(o, dirn);
+    if (proj > a1.y) return false;
+    const double dist_sqr = vdot(o, o);
+    const double term = dadd(dsub(dmul(proj, proj), dist_sqr), a2.x);
+    if (term < 1e-10) return false;
+    const double root = __dsqrt_rn(term);
+    const double f1 = dsub(-proj, root);
+    const double f2 = dadd(-proj, root);
+    const double rf = (f1 >= 0.0) ? f1 : f2;
+    if (rf < 0.0) return false;
+    *rf_out = rf;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AxisAlignedBox.ContainsPoint / ClipLineSegment (AxisAlignedBox.cs:143-149,175-216) as used by
+// SpatialSubdivision.IntersectRay (SpatialSubdivision.cs:389-401).  The six Plane objects have
+// exact axis unit normals, so Plane.IntersectLineSegment (Plane.cs:111-138) reduces, bit for bit,
+// to the per-axis quotients below (min planes first, then max planes: AxisAlignedBox.cs:22-27).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool box_contains(const double* mn, const double* mx, d3 p)
+{
+    const double e = 1e-10;
+    return dsub(mn[0], e) < p.x && p.x < dadd(mx[0], e) && dsub(mn[1], e) < p.y && p.y < dadd(mx[1], e) &&
+           dsub(mn[2], e) < p.z && p.z < dadd(mx[2], e);
+}
+
+__device__ __forceinline__ bool box_first_crossing(const double* mn, const double* mx, d3 s, d3 e, d3* pos)
+{
+    double closest = 1.7976931348623157e308;
+    const d3 span = vsub(e, s);
+    const double sv[3] = {s.x, s.y, s.z}, ev[3] = {e.x, e.y, e.z};
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int ax = k % 3;
+        // min plane k<3: (s - min) / (s - e);  max plane: (max - s) / (e - s)
+        const double num = (k < 3) ? dsub(sv[ax], mn[ax]) : dsub(mx[ax], sv[ax]);
+        const double den = (k < 3) ? dsub(sv[ax], ev[ax]) : dsub(ev[ax], sv[ax]);
+        const double lf = ddiv(num, den);
+        if (0.0 <= lf && lf <= 1.0 && lf < closest) {
+            const d3 p = vadd(s, vscale(span, lf));
+            if (box_contains(mn, mx, p)) { closest = lf; *pos = p; }
+        }
+    }
+    return closest != 1.7976931348623157e308;
+}
+
+// Returns false when the ray misses the root box (ClippedRayCount++).  On success *start is the
+// clipped start and *offset the rayFrac offset of :401.
+__device__ __forceinline__ bool reference_clip(const double* mn, const double* mx, d3* start, d3 dir, double* offset)
+{
+    const d3 s = *start;
+    const d3 end = vadd(s, vscale(dir, 10000.0));
+    const bool start_inside = box_contains(mn, mx, s);
+    const bool end_inside = box_contains(mn, mx, end);
+    *offset = 0.0;
+    if (start_inside && end_inside) return true;
+    d3 p;
+    if (!box_first_crossing(mn, mx, s, end, &p)) return false;
+    if (start_inside) return true;
+    *start = p;
+    *offset = ddiv(vlen(vsub(s, p)), vlen(dir));   // originalStart.Distance(start) / dir.Length
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 BVH traversal (candidate search only)
+// ---------------------------------------------------------------------------------------------
+struct TravRay {
+    float ox, oy, oz;      // origin near the root box
+    float ix, iy, iz;      // 1/dir
+    float nox, noy, noz;   // -o * (1/dir)
+    double t_off;          // exact-parameter value at the traversal origin
+};
+
+// Conservative entry into [mn - pad, mx + pad] along s + t*dir, t >= 0 (plain FP64, not part of
+// the reference arithmetic).  Returns false if the ray cannot touch the box.
+__device__ __forceinline__ bool entry_clip(const double* mn, const double* mx, double pad, d3 s, d3 dir, double* t_enter)
+{
+    double t0 = 0.0, t1 = 1.7976931348623157e308;
+    const double sv[3] = {s.x, s.y, s.z}, dv[3] = {dir.x, dir.y, dir.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double lo = mn[k] - pad, hi = mx[k] + pad;
+        if (dv[k] == 0.0) {
+            if (sv[k] < lo || sv[k] > hi) return false;
+        } else {
+            const double inv = 1.0 / dv[k];
+            double a = (lo - sv[k]) * inv, b = (hi - sv[k]) * inv;
+            if (a > b) { const double tmp = a; a = b; b = tmp; }
+            t0 = fmax(t0, a); t1 = fmin(t1, b);
+        }
+    }
+    if (t0 > t1 * (1.0 + 1e-12) + 1e-12) return false;
+    *t_enter = t0 > 0.0 ? t0 * (1.0 - 1e-9) : 0.0;
+    return true;
+}
+
+__device__ __forceinline__ TravRay make_trav(d3 s, d3 dir, double t_enter)
+{
+    TravRay r;
+    r.ox = (float)(s.x + dir.x * t_enter); r.oy = (float)(s.y + dir.y * t_enter); r.oz = (float)(s.z + dir.z * t_enter);
+    const float dx = (float)dir.x, dy = (float)dir.y, dz = (float)dir.z;
+    r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;      // +-inf for zero components
+    r.nox = -r.ox * r.ix; r.noy = -r.oy * r.iy; r.noz = -r.oz * r.iz;
+    // 0 * inf = NaN: fminf/fmaxf drop NaNs, so such an axis never constrains the slab
+    r.t_off = t_enter;
+    return r;
+}
+
+__device__ __forceinline__ bool slab(const TravRay& r, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                     float tcull, float* t_entry)
+{
+    const float ax = __fmaf_rn(lox, r.ix, r.nox), bx = __fmaf_rn(hix, r.ix, r.nox);
+    const float ay = __fmaf_rn(loy, r.iy, r.noy), by = __fmaf_rn(hiy, r.iy, r.noy);
+    const float az = __fmaf_rn(loz, r.iz, r.noz), bz = __fmaf_rn(hiz, r.iz, r.noz);
+    float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tcull));
+    *t_entry = tmin;
+    // slack for the rounding of the six FMAs (the boxes themselves are padded in space)
+    return tmin <= tmax * 1.00001f + 1e-6f;
+}
+
+// limit in exact-parameter units -> conservative FP32 cull distance measured from the traversal origin
+__device__ __forceinline__ float cull_from(double limit, double t_off)
+{
+    if (limit >= 1e300) return CUDART_INF_F;
+    const float v = __double2float_ru(limit - t_off);
+    return fmaxf(v, 0.0f) * 1.00002f + 1e-6f;
+}
+
+struct BestPrim { double rf; int k; int index; };
+
+// Generic BVH walk.  PRIM = 0 triangles, 1 spheres.  ANY: stop at the first primitive whose
+// exact rayFrac is <= limit (shadow rays); otherwise find the minimum rayFrac, ties to the
+// lowest list index (GeometryCollection.cs:53, SpatialSubdivision.cs:644).
+template <int PRIM, bool ANY>
+__device__ __forceinline__ bool walk(const BvhNode* __restrict__ nodes, const void* __restrict__ prims, const TravRay& tr,
+                                     d3 s, d3 dir, double limit, double any_offset, BestPrim* best, Counters* c)
+{
+    int stack[kStackEntries];
+    int sp = 0;
+    int cur = 0;
+    float tcull = cull_from(ANY ? limit : best->rf, tr.t_off);
+    for (;;) {
+        if (cur >= 0) {
+            const float4* p = reinterpret_cast<const float4*>(nodes + cur);
+            const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
+            c->node_visits++;
+            float t0, t1;
+            const bool h0 = d.z >= 0 && slab(tr, a.x, a.y, a.z, a.w, b.x, b.y, tcull, &t0);
+            const bool h1 = d.w >= 0 && slab(tr, b.z, b.w, cc.x, cc.y, cc.z, cc.w, tcull, &t1);
+            const int e0 = d.z > 0 ? -1 - (d.x * 16 + d.z) : d.x;
+            const int e1 = d.w > 0 ? -1 - (d.y * 16 + d.w) : d.y;
+            if (h0 && h1) {
+                const bool first0 = t0 <= t1;
+                stack[sp++] = first0 ? e1 : e0;
+                cur = first0 ? e0 : e1;
+                continue;
+            }
+            if (h0) { cur = e0; continue; }
+            if (h1) { cur = e1; continue; }
+        } else {
+            const int code = -1 - cur;
+            const int first = code >> 4, count = code & 15;
+            for (int i = 0; i < count; i++) {
+                const int k = first + i;
+                double rf;
+                c->prim_tests++;
+                if (PRIM == 0) {
+                    const TriRec* t = reinterpret_cast<const TriRec*>(prims) + k;
+                    if (!tri_intersect(t, s, dir, ANY ? limit : best->rf, &rf)) continue;
+                    if (ANY) {
+                        if (dadd(rf, any_offset) <= 1.0) return true;
+                        continue;
+                    }
+                    const int index = __ldg(reinterpret_cast<const int*>(t) + 31);
+                    if (rf < best->rf || (rf == best->rf && index < best->index)) {
+                        best->rf = rf; best->k = k; best->index = index;
+                        tcull = cull_from(rf, tr.t_off);
+                    }
+                } else {
+                    const SphereRec* q = reinterpret_cast<const SphereRec*>(prims) + k;
+                    c->sphere_tests++;
+                    if (!sphere_intersect(q, s, dir, &rf)) continue;
+                    if (ANY) {
+                        if (rf <= limit) return true;
+                        continue;
+                    }
+                    const int index = __ldg(reinterpret_cast<const int*>(q) + 11);
+                    if (rf < best->rf || (rf == best->rf && index < best->index)) {
+                        best->rf = rf; best->k = k; best->index = index;
+                        tcull = cull_from(rf, tr.t_off);
+                    }
+                }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return false;
+}
+
+// Linear scan (SOFTRAY_ACCEL_BRUTE): GeometryCollection.IntersectRay (GeometryCollection.cs:44-69).
+template <int PRIM, bool ANY>
+__device__ __forceinline__ bool scan(const void* __restrict__ prims, int n, d3 s, d3 dir, double limit, double any_offset,
+                                     BestPrim* best, Counters* c)
+{
+    for (int k = 0; k < n; k++) {
+        double rf;
+        c->prim_tests++;
+        if (PRIM == 0) {
+            const TriRec* t = reinterpret_cast<const TriRec*>(prims) + k;
+            if (!tri_intersect(t, s, dir, ANY ? limit : best->rf, &rf)) continue;
+            if (ANY) { if (dadd(rf, any_offset) <= 1.0) return true; continue; }
+            if (rf < best->rf) { best->rf = rf; best->k = k; best->index = k; }
+        } else {
+            const SphereRec* q = reinterpret_cast<const SphereRec*>(prims) + k;
+            c->sphere_tests++;
+            if (!sphere_intersect(q, s, dir, &rf)) continue;
+            if (ANY) { if (rf <= limit) return true; continue; }
+            if (rf < best->rf) { best->rf = rf; best->k = k; best->index = k; }
+        }
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rootGeometry: [ExtraGeometry spheres..., mesh through SpatialSubdivision | GeometryCollection]
+// ---------------------------------------------------------------------------------------------
+struct Hit {
+    double rf;
+    d3 pos, normal;
+    uint32_t color;
+    int32_t id;        // >= 0 triangle index, <= -2 sphere -(i+2)
+};
+
+constexpr double kNoHit = 1.7976931348623157e308;   // double.MaxValue (GeometryCollection.cs:48)
+
+__device__ __forceinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, d3 s, d3 dir, Hit* h,
+                                            Counters* c)
+{
+    // --- spheres (tested first in list order) ---
+    BestPrim bs; bs.rf = kNoHit; bs.k = -1; bs.index = 0x7fffffff;
+    d3 dirn = dir;
+    if (sc.n_spheres > 0) {
+        dirn = vnormalise(dir);                          // Sphere.cs:160
+        if (sc.sphere_nodes) {
+            double te;
+            if (entry_clip(sc.sph_bmin, sc.sph_bmax, 0.0, s, dirn, &te)) {
+                const TravRay tr = make_trav(s, dirn, te);
+                walk<1, false>(sc.sphere_nodes, sc.spheres, tr, s, dirn, kNoHit, 0.0, &bs, c);
+            }
+        } else {
+            scan<1, false>(sc.spheres, sc.n_spheres, s, dirn, kNoHit, 0.0, &bs, c);
+        }
+    }
+    // --- mesh ---
+    BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
+    d3 ts = s; double offset = 0.0; bool in_box = true;
+    if (m.n_tris > 0) {
+        if (subdivision) in_box = reference_clip(m.bmin, m.bmax, &ts, dir, &offset);
+        if (in_box) {
+            if (m.nodes) {
+                double te = 0.0;
+                // the clipped start already lies on/in the root box; otherwise enter it first
+                if (subdivision || entry_clip(m.bmin, m.bmax, 0.0, ts, dir, &te)) {
+                    const TravRay tr = make_trav(ts, dir, te);
+                    walk<0, false>(m.nodes, m.tris, tr, ts, dir, kNoHit, 0.0, &bt, c);
+                }
+            } else {
+                scan<0, false>(m.tris, m.n_tris, ts, dir, kNoHit, 0.0, &bt, c);
+            }
+        }
+    }
+    const double rf_tri = bt.k >= 0 ? dadd(bt.rf, offset) : kNoHit;   // SpatialSubdivision.cs:416
+    if (bt.k >= 0 && rf_tri < bs.rf) {
+        const TriRec* t = m.tris + bt.k;
+        const double2 a0 = ldg2(t, 0), a1 = ldg2(t, 1);
+        h->rf = rf_tri;
+        h->pos = vadd(ts, vscale(dir, bt.rf));             // Plane.cs:86 from the clipped start
+        h->normal = mk(a0.x, a0.y, a1.x);
+        h->color = __ldg(reinterpret_cast<const uint32_t*>(t) + 30);
+        h->id = bt.index;
+        return true;
+    }
+    if (bs.k >= 0) {
+        const SphereRec* q = sc.spheres + bs.k;
+        const double2 a0 = ldg2(q, 0), a1 = ldg2(q, 1);
+        h->rf = bs.rf;
+        h->pos = vadd(s, vscale(dirn, bs.rf));             // Sphere.cs:198
+        h->normal = vnormalise(vsub(h->pos, mk(a0.x, a0.y, a1.x)));
+        h->color = __ldg(reinterpret_cast<const uint32_t*>(q) + 10);
+        h->id = -(bs.index + 2);
+        return true;
+    }
+    return false;
+}
+
+// "shadowInfo != null && shadowInfo.rayFrac <= 1.0" (ShadowMethod.cs:171): true iff ANY primitive
+// reports a rayFrac <= 1.0, because the minimum of the reported rayFracs is what the chain returns.
+__device__ __forceinline__ bool occluded(const DevScene& sc, const DevMesh& m, int subdivision, d3 s, d3 dir, Counters* c)
+{
+    BestPrim dummy; dummy.rf = kNoHit; dummy.k = -1; dummy.index = 0;
+    if (m.n_tris > 0) {
+        d3 ts = s; double offset = 0.0;
+        bool in_box = true;
+        if (subdivision) in_box = reference_clip(m.bmin, m.bmax, &ts, dir, &offset);
+        if (in_box) {
+            // rf + offset <= 1.0 needs rf <= 1.0 - offset (+ an ulp of slack for the walk's cull)
+            const double limit = (1.0 - offset) * (1.0 + 1e-12) + 1e-300;
+            if (m.nodes) {
+                double te = 0.0;
+                if (subdivision || entry_clip(m.bmin, m.bmax, 0.0, ts, dir, &te)) {
+                    const TravRay tr = make_trav(ts, dir, te);
+                    if (walk<0, true>(m.nodes, m.tris, tr, ts, dir, limit, offset, &dummy, c)) return true;
+                }
+            } else if (scan<0, true>(m.tris, m.n_tris, ts, dir, limit, offset, &dummy, c)) return true;
+        }
+    }
+    if (sc.n_spheres > 0) {
+        const d3 dirn = vnormalise(dir);
+        if (sc.sphere_nodes) {
+            double te;
+            if (entry_clip(sc.sph_bmin, sc.sph_bmax, 0.0, s, dirn, &te) && te <= 1.0) {
+                const TravRay tr = make_trav(s, dirn, te);
+                if (walk<1, true>(sc.sphere_nodes, sc.spheres, tr, s, dirn, 1.0, 0.0, &dummy, c)) return true;
+            }
+        } else if (scan<1, true>(sc.spheres, sc.n_spheres, s, dirn, 1.0, 0.0, &dummy, c)) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ShadingMethod (ShadingMethod.cs:36-68,110-177) + Instance.TransformPosToView (Instance.cs:168-184)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t shade(const DevFrame& f, const DevInstance& in, d3 pos, d3 normal, uint32_t color)
+{
+    d3 v = mul3x4(in.M, pos);
+    const double vz = v.z;
+    v.x = dmul(ddiv(v.x, vz), f.fov_depth);
+    v.y = dmul(ddiv(v.y, vz), f.fov_depth);
+    v.z = dmul(dadd(dsub(vz, in.pos_z), 1.0), 0.5);
+    const d3 nv = mul3x3(in.M, normal);
+    d3 to_light;
+    if (f.point_lighting) to_light = vnormalise(vsub(mk(f.light_pos_view[0], f.light_pos_view[1], f.light_pos_view[2]), v));
+    else to_light = vneg(mk(f.light_dir_view[0], f.light_dir_view[1], f.light_dir_view[2]));
+    const double ldn = vdot(to_light, nv);
+    const double diffuse = fmax(0.0, ldn);
+    double specular = 0.0;
+    if (f.specular_lighting) {
+        const d3 to_cam = vnormalise(vneg(v));
+        const d3 refl = vsub(vscale(nv, dmul(2.0, ldn)), to_light);
+        const double cos_a = vdot(refl, to_cam);
+        specular = fmax(0.0, pow(cos_a, f.shininess));     // Math.Pow then Math.Max (:153-154)
+    }
+    double ch = dadd(dadd(f.ambient, diffuse), specular);   // white material, (a + d) + s
+    ch = fmin(ch, 1.0);
+    return modulate(color, to_byte(dmul(255.0, ch)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+struct PixelOut { uint32_t color; int32_t id; };
+
+__device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const DevScene& sc, const DevInstance& in,
+                                                     const DevMesh& m, const double* __restrict__ offsets, const Hit& h,
+                                                     Counters* c, unsigned int* n_shadow)
+{
+    uint32_t color = h.color;
+    c->shaded++;
+    if (f.texture3d_id) color = modulate(color, texture3d_sample(f.texture3d_id, h.pos));
+    if (f.shading) color = shade(f, in, h.pos, h.normal, color);
+    if (f.shadows) {
+        // ShadowMethod.TraceRaysForSoftShadows (ShadowMethod.cs:144-180)
+        const d3 end = vadd(h.pos, vscale(h.normal, 0.001));
+        int escaped = 0;
+        for (int i = 0; i < f.shadow_samples; i++) {
+            const d3 off = mk(offsets[3 * i], offsets[3 * i + 1], offsets[3 * i + 2]);
+            d3 start, dir;
+            if (f.point_lighting) {
+                start = vadd(mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]), off);
+                dir = vsub(end, start);
+            } else {
+                dir = mk(in.light_dir_model[0], in.light_dir_model[1], in.light_dir_model[2]);
+                start = vadd(vadd(end, vscale(dir, 1000.0)), off);
+            }
+            (*n_shadow)++;
+            if (!occluded(sc, m, f.subdivision, start, dir, c)) escaped++;
+        }
+        const double frac = ddiv((double)escaped, (double)f.shadow_samples);
+        color = modulate(color, to_byte(dmul(frac, 255.0)));
+    }
+    return color;
+}
+
+// TraceRayComplex (Renderer.cs:1850-1879) for one camera ray (+ mirror bounces, + composite instances)
+__device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const DevScene& sc, const DevInstance* __restrict__ insts,
+                                                     const double* __restrict__ offsets, const d3* starts, const d3* dirs_view_or_world,
+                                                     bool dirs_are_view, Counters* c, unsigned int* n_shadow,
+                                                     unsigned int* n_secondary, bool* hit_out)
+{
+    PixelOut out; out.color = f.background; out.id = -1;
+    Hit h; int which = 0; bool hit = false;
+    d3 dir0 = mk(0, 0, 0);
+    if (f.n_instances == 1) {
+        const DevInstance& in = insts[0];
+        dir0 = dirs_are_view ? mul3x3(in.Minv, dirs_view_or_world[0]) : dirs_view_or_world[0];
+        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, starts[0], dir0, &h, c);
+    } else {
+        // extension: nearest hit across instances, ties to the lowest instance
+        double best = kNoHit;
+        for (int i = 0; i < f.n_instances; i++) {
+            const DevInstance& in = insts[i];
+            const d3 d = mul3x3(in.Minv, dirs_view_or_world[0]);
+            Hit hi;
+            if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, mk(in.start[0], in.start[1], in.start[2]), d, &hi, c) &&
+                hi.rf < best) {
+                best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
+            }
+        }
+    }
+    *hit_out = hit;
+    if (!hit) return out;
+    const DevInstance& in = insts[which];
+    const DevMesh& m = sc.meshes[in.mesh];
+    out.id = h.id >= 0 ? in.tri_base + h.id : h.id;
+    uint32_t local[5];
+    int depth = 0;
+    local[0] = shade_and_shadow(f, sc, in, m, offsets, h, c, n_shadow);
+    uint32_t tail = 0; bool have_tail = false;
+    if (f.reflection_depth > 0 && f.n_instances == 1) {
+        d3 d = dir0;
+        for (int b = 0; b < f.reflection_depth; b++) {
+            // r = d - n * (2 (d.n)), from pos + n*0.001 (PathTracingMethod.cs:10,52)
+            const d3 r = vsub(d, vscale(h.normal, dmul(2.0, vdot(d, h.normal))));
+            const d3 rs = vadd(h.pos, vscale(h.normal, 0.001));
+            (*n_secondary)++;
+            Hit h2;
+            if (!closest_hit(sc, m, f.subdivision, rs, r, &h2, c)) { tail = f.background; have_tail = true; break; }
+            h = h2; d = r;
+            local[++depth] = shade_and_shadow(f, sc, in, m, offsets, h, c, n_shadow);
+        }
+    }
+    uint32_t acc;
+    if (have_tail) acc = mirror_blend(local[depth], tail); else acc = local[depth];
+    for (int k = depth - 1; k >= 0; k--) acc = mirror_blend(local[k], acc);
+    out.color = acc;
+    return out;
+}
+
+__global__ void __launch_bounds__(128)
+render_kernel(const DevFrame f, const DevScene sc, const DevInstance* __restrict__ g_insts, const double* __restrict__ g_offsets,
+              uint32_t* __restrict__ pixels, int32_t* __restrict__ hit_ids, unsigned int* __restrict__ tile_counter,
+              DevCounters* __restrict__ counters)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DevInstance* s_insts = reinterpret_cast<DevInstance*>(smem_raw);
+    double* s_offsets = reinterpret_cast<double*>(smem_raw + sizeof(DevInstance) * f.n_instances);
+    {
+        const int n_words = (int)(sizeof(DevInstance) * f.n_instances / 8);
+        const double* src = reinterpret_cast<const double*>(g_insts);
+        double* dst = reinterpret_cast<double*>(s_insts);
+        for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+        const int n_off = f.shadows ? 3 * f.shadow_samples : 0;
+        for (int i = threadIdx.x; i < n_off; i += blockDim.x) s_offsets[i] = g_offsets[i];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int W = f.width, H = f.height, n = f.sub_pixel_res;
+    const int n_tiles = f.tiles_x * f.tiles_y;
+    Counters c; c.node_visits = 0; c.prim_tests = 0; c.sphere_tests = 0; c.shaded = 0;
+    unsigned int n_primary = 0, n_shadow = 0, n_secondary = 0, n_hits = 0;
+
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const int ty = tile / f.tiles_x, tx = tile - ty * f.tiles_x;
+        const int col = tx * 8 + (lane & 7);
+        const int band_j = ty / f.tiles_per_band;
+        const int band_r = (ty - band_j * f.tiles_per_band) * 4 + (lane >> 3);
+        const int row = f.start_row + (f.band_index + band_j * f.band_count) * f.band_height + band_r;
+        if (col >= W || band_r >= f.band_height || row > f.end_row) continue;
+
+        PixelOut po; bool hit;
+        if (n == 1) {
+            // Renderer.cs:1728-1729
+            const d3 dir_view = mk(-dsub(ddiv((double)col, (double)W), 0.5),
+                                   dmul(-dsub(ddiv((double)row, (double)H), 0.5), f.aspect), f.fov_depth);
+            const d3 start = mk(s_insts[0].start[0], s_insts[0].start[1], s_insts[0].start[2]);
+            n_primary++;
+            po = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir_view, true, &c, &n_shadow, &n_secondary, &hit);
+            if (hit) n_hits++;
+        } else {
+            int sum_r = 0, sum_g = 0, sum_b = 0;
+            d3 focal_pt = mk(0, 0, 0);
+            const DevInstance& in0 = s_insts[0];
+            if (f.focal_blur) {
+                const d3 dir_view = mk(-dsub(ddiv((double)col, (double)W), 0.5),
+                                       dmul(-dsub(ddiv((double)row, (double)H), 0.5), f.aspect), f.fov_depth);
+                const d3 dw = mul3x3(in0.Minv, dir_view);
+                focal_pt = vadd(vscale(dw, f.focal_depth), mk(in0.start[0], in0.start[1], in0.start[2]));   // :1759
+            }
+            po.color = 0; po.id = -1; hit = false;
+            for (int sx = 0; sx < n; sx++) {
+                for (int sy = 0; sy < n; sy++) {
+                    const double fx = dsub(ddiv((double)sx, (double)(n - 1)), 0.5);     // :1767-1768
+                    const double fy = dsub(ddiv((double)sy, (double)(n - 1)), 0.5);
+                    d3 start, dir; bool is_view;
+                    if (f.focal_blur) {
+                        const d3 sv = mk(dmul(ddiv(fx, (double)W), f.focal_strength), dmul(ddiv(fy, (double)H), f.focal_strength),
+                                         -in0.pos_z);                                     // :1776-1778
+                        start = mul3x3(in0.Minv, sv);
+                        dir = vsub(focal_pt, start);                                      // :1790
+                        is_view = false;
+                    } else {
+                        start = mk(in0.start[0], in0.start[1], in0.start[2]);
+                        dir = mk(-dsub(ddiv(dadd((double)col, fx), (double)W), 0.5),
+                                 dmul(-dsub(ddiv(dadd((double)row, fy), (double)H), 0.5), f.aspect), f.fov_depth);   // :1794-1796
+                        is_view = true;
+                    }
+                    n_primary++;
+                    const PixelOut s1 = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, &n_shadow,
+                                                         &n_secondary, &hit);
+                    if (hit) n_hits++;
+                    sum_r += (s1.color >> 16) & 0xff; sum_g += (s1.color >> 8) & 0xff; sum_b += s1.color & 0xff;
+                    po.id = s1.id;
+                }
+            }
+            const int nn = n * n;
+            sum_r /= nn; sum_g /= nn; sum_b /= nn;                                        // :1820-1822
+            po.color = 0xff000000u | ((uint32_t)(sum_r & 0xff) << 16) | ((uint32_t)(sum_g & 0xff) << 8) | (uint32_t)(sum_b & 0xff);
+        }
+        const size_t idx = (size_t)row * (size_t)W + (size_t)col;
+        pixels[idx] = po.color;                                                            // Surface.DrawPixel
+        if (hit_ids) hit_ids[idx] = po.id;
+    }
+
+    // one atomic per warp per counter
+    unsigned long long v[8] = {n_primary, n_shadow, n_secondary, c.node_visits, c.prim_tests, c.sphere_tests, n_hits, c.shaded};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + k, x);
+    }
+}
+
+// host-callable launcher (sr_api.cu)
+cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets,
+                          uint32_t* d_pixels, int32_t* d_ids, unsigned int* d_tile_counter, DevCounters* d_counters,
+                          int grid_blocks, cudaStream_t stream)
+{
+    const size_t smem = sizeof(DevInstance) * (size_t)f.n_instances + (f.shadows ? sizeof(double) * 3 * (size_t)f.shadow_samples : 0);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    render_kernel<<<grid_blocks, 128, smem, stream>>>(f, sc, d_insts, d_offsets, d_pixels, d_ids, d_tile_counter, d_counters);
+    return cudaGetLastError();
+}
+
+int render_kernel_occupancy(int smem_bytes)
+{
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel, 128, (size_t)smem_bytes) != cudaSuccess) return 0;
+    return nb;
+}
+
+}  // namespace sr

@@ -141,6 +141,9 @@ class FrameParams:
     background: int = 0
     reflection_depth: int = 0
     texture3d_id: int = 0
+    band_height: int = 0  # row-band partition (one band set per GPU); 0 / band_count<=1 = all rows
+    band_count: int = 1
+    band_index: int = 0
 
     def default_light(self):
         inv = 1.0 / math.sqrt((-1.0) * (-1.0) + (-1.0) * (-1.0) + 1.0 * 1.0)  # Vector.Normalise
@@ -183,5 +186,8 @@ class FrameParams:
         f.background_argb = self.background & 0x00FFFFFF  # BackgroundColor setter (Renderer.cs:318)
         f.reflection_depth = self.reflection_depth
         f.texture3d_id = self.texture3d_id
+        f.band_height = self.band_height
+        f.band_count = self.band_count
+        f.band_index = self.band_index
         f._keepalive = inst
         return f

@@ -1,0 +1,328 @@
+"""Parity of the CUDA path (through the C ABI, softray_b200.lib) against the reference's golden
+images and against the CPU oracle.  Bars (BASELINE.json north_star): primary-hit ids bit-exact on
+non-grazing rays (|cos theta| > 1e-4), 8-bit colours within +-1 LSB on >= 99.9 % of pixels.  The
+kernel uses the reference's FP64 operations in the reference's order, so most cases are held to
+the stronger bar of ZERO differing pixels, like RendererTests.RenderAndTest (RendererTests.cs:540-543).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from softray_b200 import FrameParams, InstanceData, MeshData, SphereData, abi, synth
+from tests.util import channel_absdiff, count_diff, golden_name, path_trace_spheres, scenario
+
+pytestmark = pytest.mark.gpu
+
+COS_GRAZING = 1e-4
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from softray_b200 import lib as L
+
+    return L
+
+
+@pytest.fixture(scope="module")
+def ctx(lib):
+    c = lib.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def obj_scene(lib, ctx, obj_mesh):
+    return lib.Scene(ctx, [obj_mesh])
+
+
+@pytest.fixture(scope="module")
+def obj_oracle(obj_mesh):
+    import oracle
+
+    return oracle.Scene([obj_mesh])
+
+
+def assert_parity(got, want, exact=True, what=""):
+    """got: lib.Scene.render dict, want: oracle.Scene.render dict (with ids + aux)."""
+    gp, wp = got["pixels"], want["pixels"]
+    assert ((gp >> 24) == 0xFF).all(), what
+    n = gp.size
+    if got.get("ids") is not None and want.get("ids") is not None:
+        bad = got["ids"] != want["ids"]
+        if want.get("cos_theta") is not None:
+            cos = np.nan_to_num(np.abs(want["cos_theta"]), nan=1.0)
+            bad &= cos > COS_GRAZING
+        assert int(bad.sum()) == 0, f"{what}: {int(bad.sum())} non-grazing hit ids differ"
+    d = channel_absdiff(gp, wp)
+    n_diff = int((d > 0).sum())
+    if exact:
+        assert n_diff == 0, f"{what}: {n_diff} of {n} pixels differ (max {int(d.max())})"
+    else:
+        assert int((d > 1).sum()) <= 0.001 * n, f"{what}: {(d > 1).sum()} pixels differ by more than 1 LSB"
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own golden images
+# ------------------------------------------------------------------------------------------------
+ON_PATH = [
+    (100, dict(shading=False)),
+    (100, dict()),
+    (100, dict(sub_pixel_res=2)),
+    (100, dict(sub_pixel_res=4)),
+    (100, dict(sub_pixel_res=8)),
+    (100, dict(shadows=True)),
+    (100, dict(shading=False, shadows=True)),
+    (100, dict(shading=False, sub_pixel_res=4)),
+    (100, dict(shadows=True, sub_pixel_res=4)),
+    (100, dict(shading=False, shadows=True, sub_pixel_res=4)),
+    (100, dict(focal_blur=True, sub_pixel_res=2)),
+    (100, dict(focal_blur=True, sub_pixel_res=4)),
+    (100, dict(shading=False, focal_blur=True, sub_pixel_res=2)),
+    (100, dict(shading=False, focal_blur=True, sub_pixel_res=4)),
+    (100, dict(shadows=True, focal_blur=True, sub_pixel_res=2)),
+    (100, dict(shadows=True, focal_blur=True, sub_pixel_res=4)),
+    (100, dict(shading=False, shadows=True, focal_blur=True, sub_pixel_res=2)),
+    (100, dict(shading=False, shadows=True, focal_blur=True, sub_pixel_res=4)),
+    (50, dict(shadows=True, sub_pixel_res=4)),
+    (50, dict(shadows=True, focal_blur=True, sub_pixel_res=4)),
+]
+
+
+@pytest.mark.parametrize("res,kw", ON_PATH, ids=lambda v: str(v))
+def test_reference_goldens(fixtures, obj_scene, res, kw):
+    """Every on-path golden BMP of the reference straight from the CUDA kernel."""
+    name = golden_name(**kw)
+    golden = fixtures[f"golden/{res}x{res}/{name}"]
+    out = obj_scene.render(scenario(resolution=res, **kw))
+    assert count_diff(out["pixels"], golden) == 0, name
+    assert (out["pixels"] >> 24 == 0xFF).all()
+
+
+def test_known_answer_counters(obj_scene):
+    """10 000 primary rays, 6 716 hits, 671 600 shadow rays."""
+    out = obj_scene.render(scenario(shadows=True), want_ids=True)
+    st = out["stats"]
+    assert (st.rays_primary, st.hits_primary, st.rays_shadow) == (10000, 6716, 671600)
+    assert int((out["ids"] >= 0).sum()) == 6716 and int((out["ids"] == -1).sum()) == 3284
+    assert st.launches == 1 and st.ms_kernel > 0
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(shadows=True), dict(subdivision=False), dict(subdivision=False, shadows=True)],
+                         ids=lambda v: str(v))
+def test_brute_accel_equals_bvh(lib, ctx, obj_mesh, obj_scene, kw):
+    """SOFTRAY_ACCEL_BRUTE (GeometryCollection order) and the BVH give identical frames and ids."""
+    brute = lib.Scene(ctx, [obj_mesh], accel=abi.ACCEL_BRUTE)
+    p = scenario(resolution=96, **kw)
+    a = obj_scene.render(p, want_ids=True)
+    b = brute.render(p, want_ids=True)
+    assert count_diff(a["pixels"], b["pixels"]) == 0
+    assert (a["ids"] == b["ids"]).all()
+    brute.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle comparisons beyond the goldens
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [
+    dict(resolution=512, specular_lighting=False),                                  # configs[0]
+    dict(resolution=256, shadows=True, point_lighting=False),                       # directional light
+    dict(resolution=200, shadows=True, shadow_samples=7),
+    dict(width=333, height=77),                                                     # ragged tiles
+    dict(resolution=160, pitch_deg=35.0, yaw_deg=20.0, roll_deg=50.0, object_depth=0.3),   # camera inside the box
+    dict(resolution=128, subdivision=False, shadows=True),
+    dict(resolution=64, sub_pixel_res=3, focal_blur=True, shadows=True, focal_strength=25.0),
+], ids=lambda v: str(v))
+def test_obj3ds_against_oracle(obj_scene, obj_oracle, kw):
+    p = scenario(**kw)
+    got = obj_scene.render(p, want_ids=True)
+    want = obj_oracle.render(p, want_ids=True, want_aux=True)
+    assert_parity(got, want, what=str(kw))
+    for k in ("rays_primary", "rays_shadow", "hits_primary"):
+        assert getattr(got["stats"], k) == getattr(want["stats"], k), k
+
+
+def test_spheres_and_mesh_mixed_units(lib, ctx, obj_mesh):
+    """PathTracePrimitivesTest's scene (RendererTests.cs:251-257) without the path tracer: sphere
+    rayFrac is a distance, triangle rayFrac a multiple of |dir|, list order."""
+    import oracle
+
+    sph = path_trace_spheres()
+    for kw in (dict(shading=False), dict(), dict(shadows=True, shadow_samples=10)):
+        p = scenario(resolution=120, object_depth=3.0, **kw)
+        got = lib.Scene(ctx, [obj_mesh], sph).render(p, want_ids=True)
+        want = oracle.Scene([obj_mesh], sph).render(p, want_ids=True, want_aux=True)
+        assert_parity(got, want, what=str(kw))
+        assert int((want["ids"] <= -2).sum()) > 1000
+
+
+def test_config2_small_against_oracle(lib, ctx):
+    import oracle
+
+    meshes, spheres, p = synth.config2(width=240, height=135, shadow_samples=100, n_spheres=1000)
+    got = lib.Scene(ctx, meshes, spheres).render(p, want_ids=True)
+    want = oracle.Scene(meshes, spheres).render(p, want_ids=True, want_aux=True)
+    assert_parity(got, want, what="config2")
+    assert got["stats"].rays_shadow == want["stats"].rays_shadow == 100 * want["stats"].hits_primary
+
+
+def test_config2_brute_equals_bvh(lib, ctx):
+    meshes, spheres, p = synth.config2(width=96, height=54, shadow_samples=16, n_spheres=300)
+    a = lib.Scene(ctx, meshes, spheres).render(p, want_ids=True)
+    b = lib.Scene(ctx, meshes, spheres, accel=abi.ACCEL_BRUTE).render(p, want_ids=True)
+    assert count_diff(a["pixels"], b["pixels"]) == 0 and (a["ids"] == b["ids"]).all()
+
+
+def test_config3_small_against_oracle(lib, ctx):
+    """Shadows + 2-bounce mirror reflection + Texture3D (oracle-defined extensions)."""
+    import oracle
+
+    meshes, _, p = synth.config3(width=200, height=112, nx=121, nz=81, shadow_samples=12)
+    got = lib.Scene(ctx, meshes).render(p, want_ids=True)
+    opt = oracle.default_options(tree_max_depth=15, tree_max_per_node=25)
+    want = oracle.Scene(meshes, options=opt).render(p, want_ids=True, want_aux=True)
+    assert_parity(got, want, what="config3")
+    assert got["stats"].rays_secondary == want["stats"].rays_secondary > 0
+
+
+def test_config4_small_against_oracle(lib, ctx):
+    """Composite instances (nearest hit across instances) with 2x2 supersampling."""
+    import oracle
+
+    meshes, _, p = synth.config4(width=160, height=90, n_lon=40, n_lat=30, n_side=4, sub_pixel_res=2)
+    got = lib.Scene(ctx, meshes).render(p, want_ids=True)
+    want = oracle.Scene(meshes).render(p, want_ids=True, want_aux=True)
+    assert_parity(got, want, what="config4")
+
+
+def test_config5_small_against_oracle(lib, ctx):
+    import oracle
+
+    meshes, _, p = synth.config5(width=192, height=108, n_lon=40, n_lat=30, n_side=4, shadow_samples=3)
+    got = lib.Scene(ctx, meshes).render(p, want_ids=True)
+    want = oracle.Scene(meshes).render(p, want_ids=True, want_aux=True)
+    assert_parity(got, want, what="config5")
+
+
+# ------------------------------------------------------------------------------------------------
+# row ranges, row bands, determinism, errors
+# ------------------------------------------------------------------------------------------------
+def test_only_requested_rows_are_written(obj_scene, obj_oracle):
+    """rayTraceStartRow/EndRow (Renderer.cs:134-136): exactly those rows."""
+    p = scenario(resolution=100, start_row=37, end_row=58)
+    px = np.full((100, 100), 0xDEADBEEF, dtype=np.uint32)
+    ids = np.full((100, 100), 12345, dtype=np.int32)
+    obj_scene.render(p, pixels=px, ids=ids)
+    full = obj_oracle.render(scenario(resolution=100))["pixels"]
+    assert (px[:37] == 0xDEADBEEF).all() and (px[59:] == 0xDEADBEEF).all()
+    assert (ids[:37] == 12345).all() and (ids[59:] == 12345).all()
+    assert count_diff(px[37:59], full[37:59]) == 0
+
+
+@pytest.mark.parametrize("bands,band_height", [(2, 8), (3, 5), (8, 16), (4, 1)])
+def test_row_bands_tile_the_frame(obj_scene, bands, band_height):
+    """The union of all ranks' bands is the full frame and no band touches another's rows."""
+    W, H = 96, 83
+    full = obj_scene.render(scenario(width=W, height=H, shadows=True, shadow_samples=5), want_ids=True)
+    px = np.full((H, W), 0xDEADBEEF, dtype=np.uint32)
+    total_primary = 0
+    for r in range(bands):
+        mine = np.full((H, W), 0xDEADBEEF, dtype=np.uint32)
+        out = obj_scene.render(scenario(width=W, height=H, shadows=True, shadow_samples=5, band_height=band_height,
+                                        band_count=bands, band_index=r), pixels=mine)
+        rows = [y for y in range(H) if (y // band_height) % bands == r]
+        other = [y for y in range(H) if (y // band_height) % bands != r]
+        assert (mine[other] == 0xDEADBEEF).all()
+        px[rows] = mine[rows]
+        total_primary += out["stats"].rays_primary
+    assert count_diff(px, full["pixels"]) == 0 and (px >> 24 == 0xFF).all()
+    assert total_primary == W * H
+
+
+def test_scene_layout_is_bit_identical_across_builds(lib, ctx):
+    meshes, spheres, _ = synth.config2(n_spheres=500)
+    big = synth.height_field(101, 51)
+    fps = {lib.Scene(ctx, meshes + [big], spheres).fingerprint() for _ in range(3)}
+    assert len(fps) == 1
+    assert lib.Scene(ctx, meshes, spheres).fingerprint() not in fps
+
+
+def test_render_is_deterministic(lib, ctx):
+    meshes, spheres, p = synth.config2(width=320, height=180, shadow_samples=10)
+    sc = lib.Scene(ctx, meshes, spheres)
+    a = sc.render(p, want_ids=True)
+    b = sc.render(p, want_ids=True)
+    assert (a["pixels"] == b["pixels"]).all() and (a["ids"] == b["ids"]).all()
+    assert a["stats"].rays == b["stats"].rays
+
+
+def test_error_contracts(lib, ctx, obj_mesh):
+    """The .NET exceptions of the reference map to SOFTRAY_E_* codes (include/softray_cuda.h)."""
+    # SpatialSubdivision ctor: "A triangle vertex is outside the bounding box" (SpatialSubdivision.cs:285-295)
+    bad = MeshData(obj_mesh.verts, obj_mesh.tris, obj_mesh.argb, obj_mesh.bbox_min * 0.5, obj_mesh.bbox_max * 0.5)
+    with pytest.raises(lib.SoftRayError) as e:
+        lib.Scene(ctx, [bad])
+    assert e.value.code == abi.E_VERTEX_OUTSIDE_BBOX
+    sc = lib.Scene(ctx, [obj_mesh])
+    for kw, code in ((dict(sub_pixel_res=0), abi.E_INVALID_ARG), (dict(reflection_depth=9), abi.E_INVALID_ARG),
+                     (dict(shadows=True, shadow_samples=0), abi.E_INVALID_ARG),
+                     (dict(texture3d_id=7), abi.E_INVALID_ARG),
+                     (dict(band_count=4, band_height=4, band_index=4), abi.E_INVALID_ARG)):
+        with pytest.raises(lib.SoftRayError) as e:
+            sc.render(scenario(resolution=16, **kw))
+        assert e.value.code == code, kw
+    p = scenario(resolution=16, shadows=True)
+    p.instances = p.instances * 2
+    with pytest.raises(lib.SoftRayError) as e:
+        sc.render(p)
+    assert e.value.code == abi.E_UNSUPPORTED
+    p = scenario(resolution=16)
+    p.instances[0].mesh_id = 3
+    with pytest.raises(lib.SoftRayError) as e:
+        sc.render(p)
+    assert e.value.code == abi.E_INVALID_ARG
+
+
+def test_empty_scene_and_empty_mesh(lib, ctx):
+    """A Model with no triangles renders the background everywhere."""
+    empty = MeshData(np.zeros((0, 3)), np.zeros((0, 3), np.int32), np.zeros(0, np.uint32), [-0.5] * 3, [0.5] * 3)
+    out = lib.Scene(ctx, [empty]).render(scenario(resolution=40, shadows=True), want_ids=True)
+    assert ((out["pixels"] & 0xFFFFFF) == 0xFF00FF).all() and (out["ids"] == -1).all()
+    assert out["stats"].hits_primary == 0 and out["stats"].rays_shadow == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json sizes; the oracle only checks a sampled sub-range)
+# ------------------------------------------------------------------------------------------------
+def test_config2_full_size_rows_against_oracle(lib, ctx):
+    """configs[1] at 1920x1080 with 100 shadow rays per hit: the oracle renders three row ranges
+    through its own start_row/end_row (the reference's mechanism, Renderer.cs:134-136)."""
+    import oracle
+
+    meshes, spheres, p = synth.config2()
+    sc = lib.Scene(ctx, meshes, spheres)
+    got = sc.render(p, want_ids=True)
+    st = got["stats"]
+    assert st.rays_primary == 1920 * 1080 and st.rays_shadow == 100 * st.hits_primary
+    orc = oracle.Scene(meshes, spheres)
+    for top in (0, 539, 1078):
+        p.start_row, p.end_row = top, top + 1
+        want = orc.render(p, want_ids=True, want_aux=True)
+        sl = slice(top, top + 2)
+        sub = dict(pixels=got["pixels"][sl], ids=got["ids"][sl])
+        wsub = dict(pixels=want["pixels"][sl], ids=want["ids"][sl], cos_theta=want["cos_theta"][sl])
+        assert_parity(sub, wsub, what=f"rows {top}..{top + 1}")
+
+
+def test_config3_full_size_band_invariance(lib, ctx):
+    """1M triangles at 3840x2160 (1 shadow sample to bound the time): two interleaved bands
+    reproduce the unbanded frame exactly."""
+    meshes, _, p = synth.config3(shadow_samples=1)
+    sc = lib.Scene(ctx, meshes)
+    full = sc.render(p)
+    px = np.zeros_like(full["pixels"])
+    for r in range(2):
+        p.band_height, p.band_count, p.band_index = 32, 2, r
+        sc.render(p, pixels=px)
+    assert (px == full["pixels"]).all()
+    assert full["stats"].rays_secondary > 0 and full["stats"].hits_primary > 1_000_000
