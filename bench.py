@@ -232,7 +232,10 @@ def main():
     my_rows = multi_gpu.apply_partition(frame, rank, world, bh)
     c_frame = frame.to_c(L.softray_instance_init)
 
-    stream = torch.cuda.current_stream()
+    # a real (non-NULL) stream: the C ABI reads stream == NULL as "the context's own stream", and
+    # the CUDA events below must be recorded on the stream the kernel is launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     local_fb = torch.zeros((H, W), dtype=torch.int32, device="cuda")
     peer = None
     if world > 1 and args.gather == "peer":
@@ -307,25 +310,14 @@ def main():
                 scene.render(frame, pixels=hp, want_stats=False)
             e2e_ms = (time.perf_counter() - t) * 1e3 / e2e_steps
         else:
+            fb_view = _as_tensor(peer.ptr, H, W) if (peer is not None and rank == 0) else None
+
             def e2e_step():
-                step_device()
-                barrier()
+                assembled = step_device()           # nccl: rank 0 gets the gathered frame
+                barrier()                           # every band has landed in rank 0's HBM
                 if rank == 0:
-                    if peer is not None:
-                        abi_copy(ctx, host_px, peer.ptr, W * H * 4)
-                    else:
-                        host_px.copy_(step_result[0] if step_result[0] is not None else local_fb)
+                    host_px.copy_(fb_view if fb_view is not None else assembled)
                     torch.cuda.synchronize()
-            step_result = [None]
-
-            def abi_copy(ctx_, dst, src_ptr, nbytes):
-                import ctypes as C
-
-                cudart = C.CDLL("libcudart.so") if False else None  # noqa: F841  (torch owns the runtime)
-                torch.cuda.current_stream().synchronize()
-                # plain cudaMemcpy through torch: wrap the raw pointer as a tensor view
-                src = _as_tensor(src_ptr, H, W)
-                dst.copy_(src)
 
             for _ in range(2):
                 e2e_step()
@@ -338,7 +330,8 @@ def main():
             tt = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_ms = float(tt.item())
-        h2d = abi.Instance.__sizeof__ and (280 * len(frame.instances) + (24 * frame.shadow_samples if frame.shadows else 0))
+        # frame constants uploaded per call: DevInstance records + the area-light offsets
+        h2d = 280 * len(frame.instances) + (24 * frame.shadow_samples if frame.shadows else 0)
         e2e = {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": W * H * 4,
                "note": "softray_render (C ABI) with a pinned host framebuffer; the scene is resident "
