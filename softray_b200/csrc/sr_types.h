@@ -41,6 +41,20 @@ struct SR_ALIGN(16) SphereRec {
 };
 static_assert(sizeof(SphereRec) == 64, "SphereRec must be 64 bytes");
 
+// ---- FP32 filter records (shadow-ray any-hit search; sure answers only, see sr_render.cu) --------
+// Same formulation as the exact test: plane (n, d), then s = (pos - v1) . a, u = (pos - v1) . b with
+// a = edge2Perp / den1, b = edge1Perp / den2 folded on the host.  a1 / b1 = L1 norms (error bound).
+struct SR_ALIGN(16) TriFilt {
+    float nx, ny, nz, d;
+    float ax, ay, az, a1;
+    float bx, by, bz, b1;
+    float v1x, v1y, v1z, _pad;
+};
+static_assert(sizeof(TriFilt) == 64, "TriFilt must be 64 bytes");
+
+struct SR_ALIGN(16) SphFilt { float cx, cy, cz, r; };
+static_assert(sizeof(SphFilt) == 16, "SphFilt must be 16 bytes");
+
 // ---- BVH2 node: both children's boxes in FP32 + links = 64 bytes, four 128-bit loads ----------
 // Boxes are rounded outward and padded (sr_bvh.cpp) so that the FP32 slab test can never reject a
 // ray whose exact FP64 primitive test would hit.
@@ -59,6 +73,7 @@ constexpr int kStackEntries = 64;
 
 struct DevMesh {
     const TriRec*  tris;        // leaf order (BVH) or Model.Triangles order (brute)
+    const TriFilt* filt;        // same order as tris
     const BvhNode* nodes;       // nullptr in brute mode
     int32_t n_tris;             // number of records in `tris` (no duplication: one leaf per tri)
     int32_t n_nodes;
@@ -68,9 +83,13 @@ struct DevMesh {
 struct DevScene {
     const DevMesh*   meshes;    int32_t n_meshes;  int32_t accel;
     const SphereRec* spheres;   // leaf order (BVH) or list order (brute)
+    const SphFilt*   sph_filt;  // same order as spheres
     const BvhNode*   sphere_nodes;
     int32_t n_spheres;          int32_t n_sphere_nodes;
     double  sph_bmin[3], sph_bmax[3];   // bounds of all spheres (traversal entry clip only)
+    double  all_bmin[3], all_bmax[3];   // padded bounds of every primitive of the scene
+    float   scale;                      // largest |coordinate| of any primitive
+    int32_t _pad;
 };
 
 struct DevInstance {
@@ -98,11 +117,14 @@ struct DevFrame {
     // band_index + j * band_count, rows start_row + band * band_height ...; an unbanded frame is
     // one band of end_row - start_row + 1 rows
     int32_t band_height, band_count, band_index, tiles_per_band;
+    int32_t filter_mode;        // 0: FP32 filter + exact fallback (default); 1: exact only;
+                                // 2: verify (run both on every shadow ray, count contradictions)
+    int32_t _pad;
 };
 
 struct DevCounters {            // summed over the launch with one atomic per warp per counter
     unsigned long long rays_primary, rays_shadow, rays_secondary, node_visits, prim_tests,
-        sphere_tests, hits_primary, shaded_hits;
+        sphere_tests, hits_primary, shaded_hits, filter_tests, filter_unsure, filter_mismatch, _pad;
 };
 
 }  // namespace sr
