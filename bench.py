@@ -331,7 +331,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_ms = float(tt.item())
         # frame constants uploaded per call: DevInstance records + the area-light offsets
-        h2d = 280 * len(frame.instances) + (24 * frame.shadow_samples if frame.shadows else 0)
+        h2d = 288 * len(frame.instances) + (24 * frame.shadow_samples if frame.shadows else 0)
         e2e = {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": W * H * 4,
                "note": "softray_render (C ABI) with a pinned host framebuffer; the scene is resident "

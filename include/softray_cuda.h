@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SOFTRAY_ABI_VERSION 1
+#define SOFTRAY_ABI_VERSION 2
 #define SOFTRAY_MAX_INSTANCES 128   /* instances per frame (composite extension) */
 #define SOFTRAY_MAX_SHADOW_SAMPLES 1024
 
@@ -159,7 +159,19 @@ typedef struct softray_frame {
     int32_t band_height;
     int32_t band_count;
     int32_t band_index;
+    /* how shadow-ray queries are answered (results are identical in every mode; DESIGN.md
+     * "Filtered predicates"):  SOFTRAY_FILTER_AUTO  FP32 filter with proven error bounds, FP64
+     * reference arithmetic only for the rays the filter cannot decide (default);
+     * SOFTRAY_FILTER_OFF  every ray through the FP64 reference arithmetic;
+     * SOFTRAY_FILTER_VERIFY  both on every ray, contradictions counted in
+     * softray_stats.filter_mismatch (must stay 0). */
+    int32_t filter_mode;
+    int32_t _reserved[3];
 } softray_frame;
+
+#define SOFTRAY_FILTER_AUTO   0
+#define SOFTRAY_FILTER_OFF    1
+#define SOFTRAY_FILTER_VERIFY 2
 
 /* Counters (the reference's NumRaysFired / NumGeometryTests / NumNodeVisits, Renderer.cs:465-587)
  * and device timings of the last render. */
@@ -173,6 +185,9 @@ typedef struct softray_stats {
     uint64_t hits_primary;     /* camera rays that hit geometry                                    */
     uint64_t shaded_hits;      /* hits that went through shading (primary + reflection hits)       */
     uint64_t launches;         /* kernels launched by this call                                    */
+    uint64_t filter_tests;     /* FP32 filter primitive tests (not part of prim_tests)             */
+    uint64_t filter_unsure;    /* rays the filter could not decide (answered in FP64 instead)      */
+    uint64_t filter_mismatch;  /* SOFTRAY_FILTER_VERIFY: sure filter answers the FP64 path contradicts */
     double   ms_kernel;        /* CUDA-event time of the render kernel(s)                          */
     double   ms_h2d;           /* frame constants upload                                           */
     double   ms_d2h;           /* framebuffer (+hit ids) readback                                  */

@@ -5,7 +5,7 @@ against the values the C side reports through softray_abi_sizeof().
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK = 0
 E_INVALID_ARG = -1
@@ -18,6 +18,10 @@ E_FORMAT = -7
 
 ACCEL_BVH = 0
 ACCEL_BRUTE = 1
+
+FILTER_AUTO = 0
+FILTER_OFF = 1
+FILTER_VERIFY = 2
 
 ERROR_NAMES = {
     OK: "SOFTRAY_OK",
@@ -109,6 +113,8 @@ class Frame(C.Structure):
         ("band_height", C.c_int32),
         ("band_count", C.c_int32),
         ("band_index", C.c_int32),
+        ("filter_mode", C.c_int32),
+        ("_reserved", C.c_int32 * 3),
     ]
 
 
@@ -123,6 +129,9 @@ class Stats(C.Structure):
         ("hits_primary", C.c_uint64),
         ("shaded_hits", C.c_uint64),
         ("launches", C.c_uint64),
+        ("filter_tests", C.c_uint64),
+        ("filter_unsure", C.c_uint64),
+        ("filter_mismatch", C.c_uint64),
         ("ms_kernel", C.c_double),
         ("ms_h2d", C.c_double),
         ("ms_d2h", C.c_double),
@@ -137,7 +146,7 @@ class Stats(C.Structure):
         return self.rays_primary + self.rays_shadow + self.rays_secondary
 
 
-EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 176, "stats": 104}
+EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 192, "stats": 128}
 
 assert C.sizeof(Mesh) == EXPECTED_SIZES["mesh"]
 assert C.sizeof(Sphere) == EXPECTED_SIZES["sphere"]

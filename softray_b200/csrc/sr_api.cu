@@ -66,6 +66,7 @@ struct softray_scene {
     std::vector<int32_t> mesh_tris;    // n_tris per mesh (hit-id bases)
     uint64_t fingerprint = 1469598103934665603ull;
     size_t device_bytes = 0;
+    double all_min[3] = {1e300, 1e300, 1e300}, all_max[3] = {-1e300, -1e300, -1e300};   // every primitive
 };
 
 static thread_local std::string g_last_error;
@@ -267,6 +268,30 @@ void make_tri_rec(TriRec* t, hv v1, hv v2, hv v3, uint32_t color, int32_t index)
     t->index = index;
 }
 
+// FP32 filter record of one triangle (sr_types.h TriFilt): the exact record's quantities with the
+// two divisions folded in, rounded to nearest; a1/b1 bound the L1 norms of the rounded vectors.
+void make_tri_filt(TriFilt* f, const TriRec& t)
+{
+    std::memset(f, 0, sizeof *f);
+    f->nx = (float)t.nx; f->ny = (float)t.ny; f->nz = (float)t.nz; f->d = (float)t.d;
+    f->v1x = (float)t.v1x; f->v1y = (float)t.v1y; f->v1z = (float)t.v1z;
+    if (t.den1 == 0.0 || t.den2 == 0.0 || !std::isfinite(t.den1) || !std::isfinite(t.den2)) {
+        // zero area: every quotient of Triangle.IntersectRay is NaN or +-inf, the test never passes
+        // (Triangle.cs:42-43, TriangleTests.cs:35-44) -- unless a NaN slips through a comparison,
+        // so only an exactly-zero denominator is declared "never hit"; anything else odd goes to
+        // the exact test
+        const bool never = (t.den1 == 0.0 || t.den2 == 0.0);
+        f->a1 = never ? -1.0f : INFINITY;
+        f->b1 = f->a1;
+        return;
+    }
+    f->ax = (float)(t.e2px / t.den1); f->ay = (float)(t.e2py / t.den1); f->az = (float)(t.e2pz / t.den1);
+    f->bx = (float)(t.e1px / t.den2); f->by = (float)(t.e1py / t.den2); f->bz = (float)(t.e1pz / t.den2);
+    f->a1 = round_up((std::fabs((double)f->ax) + std::fabs((double)f->ay) + std::fabs((double)f->az)) * (1.0 + 1e-6));
+    f->b1 = round_up((std::fabs((double)f->bx) + std::fabs((double)f->by) + std::fabs((double)f->bz)) * (1.0 + 1e-6));
+    if (!std::isfinite(f->a1) || !std::isfinite(f->b1)) { f->a1 = INFINITY; f->b1 = INFINITY; }
+}
+
 inline bool box_contains(const double* mn, const double* mx, hv p)   // AxisAlignedBox.cs:143-149
 {
     const double e = 1e-10;
@@ -409,7 +434,12 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
         DevMesh& dm = meshes[(size_t)mi];
         std::memset(&dm, 0, sizeof dm);
         dm.n_tris = m.n_tris;
-        for (int k = 0; k < 3; k++) { dm.bmin[k] = m.bbox_min[k]; dm.bmax[k] = m.bbox_max[k]; }
+        for (int k = 0; k < 3; k++) {
+            dm.bmin[k] = m.bbox_min[k]; dm.bmax[k] = m.bbox_max[k];
+            dm.fmin[k] = (float)m.bbox_min[k]; dm.fmax[k] = (float)m.bbox_max[k];
+            sc->all_min[k] = std::fmin(sc->all_min[k], m.bbox_min[k]); sc->all_max[k] = std::fmax(sc->all_max[k], m.bbox_max[k]);
+        }
+        dm.scale = round_up(max_abs3(m.bbox_min, m.bbox_max));
         sc->mesh_tris.push_back(m.n_tris);
         if (m.n_tris == 0) continue;
         if (brute) {
@@ -426,6 +456,10 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
             rc = upload(sc, bvh.nodes, &dm.nodes);
             if (rc != SOFTRAY_OK) return rc;
             dm.n_nodes = (int32_t)bvh.nodes.size();
+            std::vector<TriFilt> filt((size_t)m.n_tris);
+            for (int32_t k = 0; k < m.n_tris; k++) make_tri_filt(&filt[(size_t)k], ordered[(size_t)k]);
+            rc = upload(sc, filt, &dm.filt);
+            if (rc != SOFTRAY_OK) return rc;
         }
     }
 
@@ -454,7 +488,10 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
                 lo[k] = std::fmin(lo[k], c[k] - s.r); hi[k] = std::fmax(hi[k], c[k] + s.r);
             }
         }
-        for (int k = 0; k < 3; k++) { ds.sph_bmin[k] = lo[k]; ds.sph_bmax[k] = hi[k]; }
+        for (int k = 0; k < 3; k++) {
+            ds.sph_bmin[k] = lo[k]; ds.sph_bmax[k] = hi[k];
+            sc->all_min[k] = std::fmin(sc->all_min[k], lo[k]); sc->all_max[k] = std::fmax(sc->all_max[k], hi[k]);
+        }
         if (brute) {
             int rc = upload(sc, recs, &ds.spheres);
             if (rc != SOFTRAY_OK) return rc;
@@ -536,6 +573,34 @@ struct Prepared {
     int start_row = 0, end_row = -1;
 };
 
+// A sphere reports rayFrac = distance from the ray start to the hit point (Sphere.cs:160,197) and a
+// shadow ray is occluded only by rayFrac <= 1.0 (ShadowMethod.cs:171), so a sphere further than 1.0
+// from every shadow-ray start of the frame can never occlude.  Conservative: 0 only when proven.
+int32_t spheres_can_shadow(const softray_scene* scene, const DevFrame& f, const DevInstance& d, const double* offsets)
+{
+    const DevScene& ds = scene->dev;
+    const double margin = 1e-6;
+    if (f.point_lighting) {
+        for (int i = 0; i < f.shadow_samples; i++) {
+            double dist2 = 0.0;   // squared distance from start_i = light + offset_i to the sphere bounds
+            for (int k = 0; k < 3; k++) {
+                const double s = d.light_pos_model[k] + offsets[3 * i + k];
+                const double g = s < ds.sph_bmin[k] ? ds.sph_bmin[k] - s : (s > ds.sph_bmax[k] ? s - ds.sph_bmax[k] : 0.0);
+                dist2 += g * g;
+            }
+            if (!(std::sqrt(dist2) > 1.0 + margin)) return 1;
+        }
+        return 0;
+    }
+    // directional: start = end + dir * 1000 + offset with `end` within 0.001 of some primitive
+    double diag2 = 0.0;
+    for (int k = 0; k < 3; k++) { const double e = scene->all_max[k] - scene->all_min[k]; diag2 += e * e; }
+    const double len = std::sqrt(d.light_dir_model[0] * d.light_dir_model[0] + d.light_dir_model[1] * d.light_dir_model[1] +
+                                 d.light_dir_model[2] * d.light_dir_model[2]);
+    const double nearest = 1000.0 * len - 0.2 * (1.0 + 1e-9) - 0.001 * (1.0 + 1e-9) - std::sqrt(diag2);
+    return nearest > 1.0 + margin ? 0 : 1;
+}
+
 int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_frame* fr, Prepared* p)
 {
     if (!fr->instances) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: frame.instances is NULL");
@@ -550,6 +615,8 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
         return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: band_index out of range");
     if (fr->texture3d_id != 0 && fr->texture3d_id != 1)
         return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: unknown texture3d_id");
+    if (fr->filter_mode < SOFTRAY_FILTER_AUTO || fr->filter_mode > SOFTRAY_FILTER_VERIFY)
+        return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: unknown filter_mode");
     if (fr->n_instances > 1 && (scene->dev.n_spheres > 0 || fr->shadows || (fr->focal_blur && fr->sub_pixel_res > 1) ||
                                 fr->reflection_depth))
         return fail(ctx, SOFTRAY_E_UNSUPPORTED,
@@ -588,6 +655,13 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     f.band_height = banded ? fr->band_height : rows;
     f.band_count = banded ? fr->band_count : 1;
     f.band_index = banded ? fr->band_index : 0;
+    // the FP32 filter needs the BVH layout (filter records live in leaf order)
+    f.filter_mode = scene->dev.accel == SOFTRAY_ACCEL_BVH ? fr->filter_mode : SOFTRAY_FILTER_OFF;
+
+    if (f.shadows && (ctx->cached_samples != f.shadow_samples || ctx->cached_seed != fr->random_seed)) {
+        area_light_offsets(fr->random_seed, f.shadow_samples, ctx->h_offsets);
+        ctx->cached_samples = f.shadow_samples; ctx->cached_seed = fr->random_seed;
+    }
 
     int32_t base = 0;
     for (int32_t i = 0; i < fr->n_instances; i++) {
@@ -611,10 +685,7 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
         d.mesh = in.mesh_id;
         d.tri_base = base;
         base += scene->mesh_tris[(size_t)in.mesh_id];
-    }
-    if (f.shadows && (ctx->cached_samples != f.shadow_samples || ctx->cached_seed != fr->random_seed)) {
-        area_light_offsets(fr->random_seed, f.shadow_samples, ctx->h_offsets);
-        ctx->cached_samples = f.shadow_samples; ctx->cached_seed = fr->random_seed;
+        d.sph_can_shadow = (f.shadows && scene->dev.n_spheres > 0) ? spheres_can_shadow(scene, f, d, ctx->h_offsets) : 0;
     }
 
     // one warp per 8x4-pixel tile, pulled from an atomic queue by persistent warps
@@ -665,6 +736,7 @@ int collect_stats(softray_ctx* ctx, cudaStream_t stream, softray_stats* st, bool
     st->rays_primary = c.rays_primary; st->rays_shadow = c.rays_shadow; st->rays_secondary = c.rays_secondary;
     st->node_visits = c.node_visits; st->prim_tests = c.prim_tests; st->sphere_tests = c.sphere_tests;
     st->hits_primary = c.hits_primary; st->shaded_hits = c.shaded_hits;
+    st->filter_tests = c.filter_tests; st->filter_unsure = c.filter_unsure; st->filter_mismatch = c.filter_mismatch;
     st->launches = 1;
     float ms = 0.f;
     SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); st->ms_h2d = ms;

@@ -89,7 +89,7 @@ __device__ __forceinline__ uint32_t mirror_blend(uint32_t local, uint32_t refl)
     return 0xff000000u | (r << 16) | (g << 8) | b;
 }
 
-struct Counters { unsigned int node_visits, prim_tests, sphere_tests, shaded; };
+struct Counters { unsigned int node_visits, prim_tests, sphere_tests, shaded, filter_tests, filter_unsure, filter_mismatch; };
 
 // ---------------------------------------------------------------------------------------------
 // exact primitive tests
@@ -358,6 +358,167 @@ __device__ __forceinline__ bool scan(const void* __restrict__ prims, int n, d3 s
 }
 
 // ---------------------------------------------------------------------------------------------
+// FP32 filtered predicate for shadow rays (DESIGN.md "Filtered predicates")
+//
+// A shadow ray only needs a boolean: does ANY triangle report rayFrac (+ clip offset) <= 1.0
+// (ShadowMethod.cs:171).  The filter evaluates the same plane / barycentric formulation in FP32
+// (FMA allowed) together with a running bound on how far each FP32 quantity can be from the value
+// the FP64 reference arithmetic produces, and answers only when every comparison clears its bound:
+//     0 = surely no triangle occludes, 1 = surely one does, 2 = cannot tell (-> exact FP64 path).
+// The ray is parametrised backwards from its far end:  P(tau) = anchor + g * tau,  g = -dir,
+// anchor = start + dir (the shadow receiver `end`, which lies on the geometry, so every FP32 operand
+// stays of the order of the scene size whatever the distance of the light).  rayFrac_total = 1 - tau:
+//     rayFrac + offset <= 1.0          <=>  tau >= 0
+//     hit not before the clipped start <=>  tau <= min(1, tau_out)   (tau_out: where P leaves the root
+//                                            box; SpatialSubdivision.cs:389-401 moves the start there)
+// u = 2^-24.  First-order bounds (each constant below is >= 1.5x the derived one):
+//     |g.n  - exact| <= 5u |g|_1            (|n_k| <= 1)                     used: 8u
+//     |num  - exact| <= 4u |d| + 5u |o|_1   (num = d - o.n)                  used: 8u
+//     |tau  - exact| <= (E_num + |tau| E_gn) / gn * 1.07 + 3u |tau|          used: 1.1, 4u
+//     |w_k  - exact| <= |g|_inf E_tau + 3u (|o|_inf + |g|_inf |tau|) + 2u V  (w = P - v1, V = max |coord|)
+//     |s    - exact| <= a1 (E_w + 4u W)  <= a1 (|g|_inf E_tau + 7u (|o|_inf + |g|_inf |tau| + V))   used: 12u
+// ---------------------------------------------------------------------------------------------
+constexpr float kU = 5.9604644775390625e-8f;   // 2^-24
+
+struct FRay {
+    float ox, oy, oz;         // anchor
+    float gx, gy, gz;         // direction of increasing tau
+    float ix, iy, iz;         // 1 / g
+    float nox, noy, noz;      // -o / g
+    float g1, ginf, o1, oinf; // |g|_1, |g|_inf, |o|_1, |o|_inf
+    float tmax_lo, tmax_hi;   // bracket of the largest admissible tau
+    float tcull;              // traversal cull distance (>= tmax_hi, with slack)
+};
+
+// 0: no triangle of the mesh can be hit, 1: traverse, 2: cannot tell
+__device__ __forceinline__ int fray_setup(const DevMesh& m, int subdivision, d3 anchor, d3 dir, FRay* r)
+{
+    r->ox = __double2float_rn(anchor.x); r->oy = __double2float_rn(anchor.y); r->oz = __double2float_rn(anchor.z);
+    r->gx = -__double2float_rn(dir.x); r->gy = -__double2float_rn(dir.y); r->gz = -__double2float_rn(dir.z);
+    const float agx = fabsf(r->gx), agy = fabsf(r->gy), agz = fabsf(r->gz);
+    const float aox = fabsf(r->ox), aoy = fabsf(r->oy), aoz = fabsf(r->oz);
+    r->g1 = agx + agy + agz; r->ginf = fmaxf(agx, fmaxf(agy, agz));
+    r->o1 = aox + aoy + aoz; r->oinf = fmaxf(aox, fmaxf(aoy, aoz));
+    // an exactly axis-parallel or degenerate direction or a non-finite operand: exact path
+    if (!(fminf(agx, fminf(agy, agz)) > 1e-30f) || !(r->ginf < 1e30f) || !(r->oinf < 1e30f)) return 2;
+    r->ix = __fdiv_rn(1.0f, r->gx); r->iy = __fdiv_rn(1.0f, r->gy); r->iz = __fdiv_rn(1.0f, r->gz);
+    r->nox = -r->ox * r->ix; r->noy = -r->oy * r->iy; r->noz = -r->oz * r->iz;
+    // the root box along tau, with a per-axis bound on every crossing:
+    //   c_k = (plane_k - o_k) / g_k;  |c_k - exact| <= |1/g_k| u (|plane_k| + |o_k|) + 3u |c_k|        used: 2u, 4u
+    // (+ 4e-10: the 1e-10 tolerance of AxisAlignedBox.ContainsPoint, AxisAlignedBox.cs:9,143-149)
+    const float fxa = (m.fmin[0] - r->ox) * r->ix, fxb = (m.fmax[0] - r->ox) * r->ix;
+    const float fya = (m.fmin[1] - r->oy) * r->iy, fyb = (m.fmax[1] - r->oy) * r->iy;
+    const float fza = (m.fmin[2] - r->oz) * r->iz, fzb = (m.fmax[2] - r->oz) * r->iz;
+    const float farx = fmaxf(fxa, fxb), fary = fmaxf(fya, fyb), farz = fmaxf(fza, fzb);
+    const float nearx = fminf(fxa, fxb), neary = fminf(fya, fyb), nearz = fminf(fza, fzb);
+    const float px = fabsf(r->ix) * ((2.0f * kU) * (m.scale + aox) + 4e-10f);
+    const float py = fabsf(r->iy) * ((2.0f * kU) * (m.scale + aoy) + 4e-10f);
+    const float pz = fabsf(r->iz) * ((2.0f * kU) * (m.scale + aoz) + 4e-10f);
+    const float out_lo = fminf(farx - (px + (4.0f * kU) * fabsf(farx)),
+                               fminf(fary - (py + (4.0f * kU) * fabsf(fary)), farz - (pz + (4.0f * kU) * fabsf(farz))));
+    const float out_hi = fminf(farx + (px + (4.0f * kU) * fabsf(farx)),
+                               fminf(fary + (py + (4.0f * kU) * fabsf(fary)), farz + (pz + (4.0f * kU) * fabsf(farz))));
+    const float in_lo = fmaxf(nearx - (px + (4.0f * kU) * fabsf(nearx)),
+                              fmaxf(neary - (py + (4.0f * kU) * fabsf(neary)), nearz - (pz + (4.0f * kU) * fabsf(nearz))));
+    if (!(out_hi >= 0.0f)) return out_hi < 0.0f ? 0 : 2;      // the box lies wholly behind the anchor (NaN: cannot tell)
+    r->tmax_hi = fminf(1.0f, out_hi);
+    if (in_lo > r->tmax_hi) return 0;                         // the box is missed, or lies beyond the ray's start
+    // an anchor far from the mesh: the BVH pad (sr_bvh.cpp) assumes an origin within ~2x its scale
+    if (!(r->oinf <= 2.0f * m.scale) || !(in_lo == in_lo)) return 2;
+    r->tmax_lo = subdivision ? fminf(1.0f, out_lo) : 1.0f;
+    r->tcull = r->tmax_hi * 1.00002f + 1e-6f;
+    return 1;
+}
+
+__device__ __forceinline__ bool fslab(const FRay& r, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                      float* t_entry)
+{
+    const float ax = __fmaf_rn(lox, r.ix, r.nox), bx = __fmaf_rn(hix, r.ix, r.nox);
+    const float ay = __fmaf_rn(loy, r.iy, r.noy), by = __fmaf_rn(hiy, r.iy, r.noy);
+    const float az = __fmaf_rn(loz, r.iz, r.noz), bz = __fmaf_rn(hiz, r.iz, r.noz);
+    const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), r.tcull));
+    *t_entry = tmin;
+    return tmin <= tmax * 1.00001f + 1e-6f;      // same slack as slab(): the boxes are padded in space
+}
+
+// 0 surely missed (or outside [0, tmax]), 1 surely hit inside (0, tmax), 2 cannot tell
+__device__ __forceinline__ int tri_filter(const TriFilt* __restrict__ t, const FRay& r, float V)
+{
+    const float4* p = reinterpret_cast<const float4*>(t);
+    const float4 q0 = __ldg(p);                                          // n, d
+    const float gn = __fmaf_rn(r.gz, q0.z, __fmaf_rn(r.gy, q0.y, r.gx * q0.x));
+    const float e_gn = (8.0f * kU) * r.g1;
+    if (!(gn > e_gn)) return gn < -e_gn ? 0 : 2;                         // dir.n >= 0: one-sided (Plane.cs:75)
+    const float num = __fmaf_rn(-r.oz, q0.z, __fmaf_rn(-r.oy, q0.y, __fmaf_rn(-r.ox, q0.x, q0.w)));
+    const float e_num = (8.0f * kU) * (fabsf(q0.w) + r.o1);
+    if (num < -e_num) return 0;                                          // tau < 0: rayFrac > 1
+    if (!(gn > 16.0f * e_gn)) return 2;                                  // grazing: tau not trustworthy
+    const float rg = __fdividef(1.0f, gn);
+    const float tau = num * rg;
+    const float e_tau = (e_num + fabsf(tau) * e_gn) * rg * 1.1f + (4.0f * kU) * fabsf(tau);
+    if (tau - e_tau > r.tmax_hi) return 0;                               // before the (clipped) start
+    const float4 q3 = __ldg(p + 3);                                      // v1, -
+    const float wx = __fmaf_rn(r.gx, tau, r.ox) - q3.x, wy = __fmaf_rn(r.gy, tau, r.oy) - q3.y,
+                wz = __fmaf_rn(r.gz, tau, r.oz) - q3.z;
+    const float4 q1 = __ldg(p + 1);                                      // a, a1
+    if (q1.w < 0.0f) return 0;                                           // zero-area triangle: never hit
+    const float k = r.ginf * e_tau + (12.0f * kU) * (r.oinf + r.ginf * fabsf(tau) + V);
+    const float sN = __fmaf_rn(wz, q1.z, __fmaf_rn(wy, q1.y, wx * q1.x));
+    const float e_s = q1.w * k;
+    if (sN < -e_s || sN > 1.0f + e_s) return 0;
+    const float4 q2 = __ldg(p + 2);                                      // b, b1
+    const float uu = __fmaf_rn(wz, q2.z, __fmaf_rn(wy, q2.y, wx * q2.x));
+    const float e_u = q2.w * k;
+    if (uu < -e_u) return 0;
+    const float sum = sN + uu, e_sum = e_s + e_u + 4.0f * kU;
+    if (sum > 1.0f + e_sum) return 0;
+    if (num > e_num && tau + e_tau < r.tmax_lo && sN > e_s && uu > e_u && sum < 1.0f - e_sum) return 1;
+    return 2;                                                            // also every NaN / inf case
+}
+
+// BVH walk with the filter at the leaves.  0 surely clear, 1 surely occluded, 2 cannot tell.
+__device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, const FRay& r,
+                                               float V, Counters* c)
+{
+    int stack[kStackEntries];
+    int sp = 0;
+    int cur = 0;
+    for (;;) {
+        if (cur >= 0) {
+            const float4* p = reinterpret_cast<const float4*>(nodes + cur);
+            const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
+            c->node_visits++;
+            float t0, t1;
+            const bool h0 = d.z >= 0 && fslab(r, a.x, a.y, a.z, a.w, b.x, b.y, &t0);
+            const bool h1 = d.w >= 0 && fslab(r, b.z, b.w, cc.x, cc.y, cc.z, cc.w, &t1);
+            const int e0 = d.z > 0 ? -1 - (d.x * 16 + d.z) : d.x;
+            const int e1 = d.w > 0 ? -1 - (d.y * 16 + d.w) : d.y;
+            if (h0 && h1) {
+                const bool first0 = t0 <= t1;
+                stack[sp++] = first0 ? e1 : e0;
+                cur = first0 ? e0 : e1;
+                continue;
+            }
+            if (h0) { cur = e0; continue; }
+            if (h1) { cur = e1; continue; }
+        } else {
+            const int code = -1 - cur;
+            const int first = code >> 4, count = code & 15;
+            for (int i = 0; i < count; i++) {
+                c->filter_tests++;
+                const int res = tri_filter(filt + first + i, r, V);
+                if (res) return res;
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // rootGeometry: [ExtraGeometry spheres..., mesh through SpatialSubdivision | GeometryCollection]
 // ---------------------------------------------------------------------------------------------
 struct Hit {
@@ -369,8 +530,8 @@ struct Hit {
 
 constexpr double kNoHit = 1.7976931348623157e308;   // double.MaxValue (GeometryCollection.cs:48)
 
-__device__ __forceinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, d3 s, d3 dir, Hit* h,
-                                            Counters* c)
+__device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, d3 s, d3 dir, Hit* h,
+                                         Counters* c)
 {
     // --- spheres (tested first in list order) ---
     BestPrim bs; bs.rf = kNoHit; bs.k = -1; bs.index = 0x7fffffff;
@@ -431,36 +592,41 @@ __device__ __forceinline__ bool closest_hit(const DevScene& sc, const DevMesh& m
 
 // "shadowInfo != null && shadowInfo.rayFrac <= 1.0" (ShadowMethod.cs:171): true iff ANY primitive
 // reports a rayFrac <= 1.0, because the minimum of the reported rayFracs is what the chain returns.
-__device__ __forceinline__ bool occluded(const DevScene& sc, const DevMesh& m, int subdivision, d3 s, d3 dir, Counters* c)
+// Exact (reference arithmetic) versions, one per primitive kind.
+__device__ __noinline__ bool occluded_mesh(const DevMesh& m, int subdivision, d3 s, d3 dir, Counters* c)
 {
     BestPrim dummy; dummy.rf = kNoHit; dummy.k = -1; dummy.index = 0;
-    if (m.n_tris > 0) {
-        d3 ts = s; double offset = 0.0;
-        bool in_box = true;
-        if (subdivision) in_box = reference_clip(m.bmin, m.bmax, &ts, dir, &offset);
-        if (in_box) {
-            // rf + offset <= 1.0 needs rf <= 1.0 - offset (+ an ulp of slack for the walk's cull)
-            const double limit = (1.0 - offset) * (1.0 + 1e-12) + 1e-300;
-            if (m.nodes) {
-                double te = 0.0;
-                if (subdivision || entry_clip(m.bmin, m.bmax, 0.0, ts, dir, &te)) {
-                    const TravRay tr = make_trav(ts, dir, te);
-                    if (walk<0, true>(m.nodes, m.tris, tr, ts, dir, limit, offset, &dummy, c)) return true;
-                }
-            } else if (scan<0, true>(m.tris, m.n_tris, ts, dir, limit, offset, &dummy, c)) return true;
+    if (m.n_tris <= 0) return false;
+    d3 ts = s; double offset = 0.0;
+    if (subdivision && !reference_clip(m.bmin, m.bmax, &ts, dir, &offset)) return false;
+    // rf + offset <= 1.0 needs rf <= 1.0 - offset (+ an ulp of slack for the walk's cull)
+    const double limit = (1.0 - offset) * (1.0 + 1e-12) + 1e-300;
+    if (m.nodes) {
+        double te = 0.0;
+        // the clipped start already lies on/in the root box; otherwise enter it first
+        if (subdivision || entry_clip(m.bmin, m.bmax, 0.0, ts, dir, &te)) {
+            const TravRay tr = make_trav(ts, dir, te);
+            return walk<0, true>(m.nodes, m.tris, tr, ts, dir, limit, offset, &dummy, c);
         }
+        return false;
     }
-    if (sc.n_spheres > 0) {
-        const d3 dirn = vnormalise(dir);
-        if (sc.sphere_nodes) {
-            double te;
-            if (entry_clip(sc.sph_bmin, sc.sph_bmax, 0.0, s, dirn, &te) && te <= 1.0) {
-                const TravRay tr = make_trav(s, dirn, te);
-                if (walk<1, true>(sc.sphere_nodes, sc.spheres, tr, s, dirn, 1.0, 0.0, &dummy, c)) return true;
-            }
-        } else if (scan<1, true>(sc.spheres, sc.n_spheres, s, dirn, 1.0, 0.0, &dummy, c)) return true;
+    return scan<0, true>(m.tris, m.n_tris, ts, dir, limit, offset, &dummy, c);
+}
+
+__device__ __noinline__ bool occluded_spheres(const DevScene& sc, d3 s, d3 dir, Counters* c)
+{
+    BestPrim dummy; dummy.rf = kNoHit; dummy.k = -1; dummy.index = 0;
+    if (sc.n_spheres <= 0) return false;
+    const d3 dirn = vnormalise(dir);
+    if (sc.sphere_nodes) {
+        double te;
+        if (entry_clip(sc.sph_bmin, sc.sph_bmax, 0.0, s, dirn, &te) && te <= 1.0) {
+            const TravRay tr = make_trav(s, dirn, te);
+            return walk<1, true>(sc.sphere_nodes, sc.spheres, tr, s, dirn, 1.0, 0.0, &dummy, c);
+        }
+        return false;
     }
-    return false;
+    return scan<1, true>(sc.spheres, sc.n_spheres, s, dirn, 1.0, 0.0, &dummy, c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -496,6 +662,28 @@ __device__ __forceinline__ uint32_t shade(const DevFrame& f, const DevInstance& 
 // ---------------------------------------------------------------------------------------------
 struct PixelOut { uint32_t color; int32_t id; };
 
+// One shadow ray of ShadowMethod.TraceRaysForSoftShadows (ShadowMethod.cs:147-177): sample i of the
+// area light towards `end`.  Reference arithmetic for start / dir; exact versions on demand.
+__device__ __forceinline__ void shadow_ray(const DevFrame& f, const DevInstance& in, const double* __restrict__ offsets, d3 end,
+                                           int i, d3* start, d3* dir)
+{
+    const d3 off = mk(offsets[3 * i], offsets[3 * i + 1], offsets[3 * i + 2]);
+    if (f.point_lighting) {
+        *start = vadd(mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]), off);
+        *dir = vsub(end, *start);
+    } else {
+        *dir = mk(in.light_dir_model[0], in.light_dir_model[1], in.light_dir_model[2]);
+        *start = vadd(vadd(end, vscale(*dir, 1000.0)), off);
+    }
+}
+
+__device__ __forceinline__ bool occluded_exact(const DevScene& sc, const DevInstance& in, const DevMesh& m, int subdivision,
+                                               d3 start, d3 dir, Counters* c)
+{
+    if (occluded_mesh(m, subdivision, start, dir, c)) return true;
+    return in.sph_can_shadow && occluded_spheres(sc, start, dir, c);
+}
+
 __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const DevScene& sc, const DevInstance& in,
                                                      const DevMesh& m, const double* __restrict__ offsets, const Hit& h,
                                                      Counters* c, unsigned int* n_shadow)
@@ -508,20 +696,47 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
         // ShadowMethod.TraceRaysForSoftShadows (ShadowMethod.cs:144-180)
         const d3 end = vadd(h.pos, vscale(h.normal, 0.001));
         int escaped = 0;
-        for (int i = 0; i < f.shadow_samples; i++) {
-            const d3 off = mk(offsets[3 * i], offsets[3 * i + 1], offsets[3 * i + 2]);
-            d3 start, dir;
-            if (f.point_lighting) {
-                start = vadd(mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]), off);
-                dir = vsub(end, start);
+        const int n = f.shadow_samples;
+        const bool use_filter = f.filter_mode != 1 && m.nodes != nullptr && m.n_tris > 0;
+        *n_shadow += (unsigned int)n;
+        // 32 samples at a time: the filter answers most rays; the undecided ones are collected in a
+        // bit mask and answered by the exact path afterwards, when the lanes of the warp that have
+        // any can run it together
+        for (int base = 0; base < n; base += 32) {
+            const int cnt = min(32, n - base);
+            unsigned int pending = 0;
+            if (use_filter) {
+                for (int j = 0; j < cnt; j++) {
+                    d3 start, dir;
+                    shadow_ray(f, in, offsets, end, base + j, &start, &dir);
+                    // anchor = the ray's far end (start + dir): `end` itself for a point light
+                    const d3 anchor = f.point_lighting ? end : vadd(start, dir);
+                    FRay r;
+                    int res = fray_setup(m, f.subdivision, anchor, dir, &r);
+                    if (res == 1) res = walk_filter_any(m.nodes, m.filt, r, m.scale, c);
+                    if (f.filter_mode == 2) {
+                        const bool occ = occluded_mesh(m, f.subdivision, start, dir, c);
+                        if ((res == 0 && occ) || (res == 1 && !occ)) c->filter_mismatch++;
+                        if (res == 2) c->filter_unsure++;
+                        res = occ ? 1 : 0;
+                    }
+                    if (res == 0 && in.sph_can_shadow) res = occluded_spheres(sc, start, dir, c) ? 1 : 0;
+                    if (res == 0) escaped++;
+                    else if (res == 2) pending |= 1u << j;
+                }
             } else {
-                dir = mk(in.light_dir_model[0], in.light_dir_model[1], in.light_dir_model[2]);
-                start = vadd(vadd(end, vscale(dir, 1000.0)), off);
+                pending = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
             }
-            (*n_shadow)++;
-            if (!occluded(sc, m, f.subdivision, start, dir, c)) escaped++;
+            while (pending) {
+                const int j = __ffs((int)pending) - 1;
+                pending &= pending - 1;
+                d3 start, dir;
+                shadow_ray(f, in, offsets, end, base + j, &start, &dir);
+                if (use_filter) c->filter_unsure++;
+                if (!occluded_exact(sc, in, m, f.subdivision, start, dir, c)) escaped++;
+            }
         }
-        const double frac = ddiv((double)escaped, (double)f.shadow_samples);
+        const double frac = ddiv((double)escaped, (double)n);
         color = modulate(color, to_byte(dmul(frac, 255.0)));
     }
     return color;
@@ -583,7 +798,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
 }
 
 __global__ void __launch_bounds__(128)
-render_kernel(const DevFrame f, const DevScene sc, const DevInstance* __restrict__ g_insts, const double* __restrict__ g_offsets,
+render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevScene sc, const DevInstance* __restrict__ g_insts, const double* __restrict__ g_offsets,
               uint32_t* __restrict__ pixels, int32_t* __restrict__ hit_ids, unsigned int* __restrict__ tile_counter,
               DevCounters* __restrict__ counters)
 {
@@ -604,6 +819,7 @@ render_kernel(const DevFrame f, const DevScene sc, const DevInstance* __restrict
     const int W = f.width, H = f.height, n = f.sub_pixel_res;
     const int n_tiles = f.tiles_x * f.tiles_y;
     Counters c; c.node_visits = 0; c.prim_tests = 0; c.sphere_tests = 0; c.shaded = 0;
+    c.filter_tests = 0; c.filter_unsure = 0; c.filter_mismatch = 0;
     unsigned int n_primary = 0, n_shadow = 0, n_secondary = 0, n_hits = 0;
 
     for (;;) {
@@ -673,9 +889,10 @@ render_kernel(const DevFrame f, const DevScene sc, const DevInstance* __restrict
     }
 
     // one atomic per warp per counter
-    unsigned long long v[8] = {n_primary, n_shadow, n_secondary, c.node_visits, c.prim_tests, c.sphere_tests, n_hits, c.shaded};
+    unsigned long long v[11] = {n_primary, n_shadow, n_secondary, c.node_visits, c.prim_tests, c.sphere_tests, n_hits, c.shaded,
+                                c.filter_tests, c.filter_unsure, c.filter_mismatch};
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 11; k++) {
         unsigned long long x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + k, x);

@@ -41,9 +41,12 @@ struct SR_ALIGN(16) SphereRec {
 };
 static_assert(sizeof(SphereRec) == 64, "SphereRec must be 64 bytes");
 
-// ---- FP32 filter records (shadow-ray any-hit search; sure answers only, see sr_render.cu) --------
-// Same formulation as the exact test: plane (n, d), then s = (pos - v1) . a, u = (pos - v1) . b with
-// a = edge2Perp / den1, b = edge1Perp / den2 folded on the host.  a1 / b1 = L1 norms (error bound).
+// ---- FP32 filter record (DESIGN.md "Filtered predicates"; tri_filter in sr_render.cu) -----------
+// The same formulation as the exact test, rounded to FP32: plane (n, d), then
+// s = (pos - v1) . a and u = (pos - v1) . b with a = edge2Perp / den1, b = edge1Perp / den2 folded on
+// the host in FP64.  a1 / b1 = L1 norms of the ROUNDED a / b, rounded up: they scale the error
+// bound of s / u.  a1 < 0 marks a triangle the exact test can never hit (zero area: Triangle.cs:42-43
+// makes every quotient NaN); a1 = +inf one the filter must always hand to the exact test.
 struct SR_ALIGN(16) TriFilt {
     float nx, ny, nz, d;
     float ax, ay, az, a1;
@@ -51,9 +54,6 @@ struct SR_ALIGN(16) TriFilt {
     float v1x, v1y, v1z, _pad;
 };
 static_assert(sizeof(TriFilt) == 64, "TriFilt must be 64 bytes");
-
-struct SR_ALIGN(16) SphFilt { float cx, cy, cz, r; };
-static_assert(sizeof(SphFilt) == 16, "SphFilt must be 16 bytes");
 
 // ---- BVH2 node: both children's boxes in FP32 + links = 64 bytes, four 128-bit loads ----------
 // Boxes are rounded outward and padded (sr_bvh.cpp) so that the FP32 slab test can never reject a
@@ -78,18 +78,17 @@ struct DevMesh {
     int32_t n_tris;             // number of records in `tris` (no duplication: one leaf per tri)
     int32_t n_nodes;
     double  bmin[3], bmax[3];   // root AxisAlignedBox = Model.Min/Max (Renderer.cs:1487)
+    float   fmin[3], fmax[3];   // the same box rounded to FP32 (nearest)
+    float   scale;              // largest |coordinate| of bmin/bmax, rounded up
+    int32_t _pad;
 };
 
 struct DevScene {
     const DevMesh*   meshes;    int32_t n_meshes;  int32_t accel;
     const SphereRec* spheres;   // leaf order (BVH) or list order (brute)
-    const SphFilt*   sph_filt;  // same order as spheres
     const BvhNode*   sphere_nodes;
     int32_t n_spheres;          int32_t n_sphere_nodes;
     double  sph_bmin[3], sph_bmax[3];   // bounds of all spheres (traversal entry clip only)
-    double  all_bmin[3], all_bmax[3];   // padded bounds of every primitive of the scene
-    float   scale;                      // largest |coordinate| of any primitive
-    int32_t _pad;
 };
 
 struct DevInstance {
@@ -101,6 +100,8 @@ struct DevInstance {
     double light_dir_model[3];  // directionalLight_dir_model (Renderer.cs:1513)
     int32_t mesh;               // index into DevScene.meshes
     int32_t tri_base;           // flattened hit-id base
+    int32_t sph_can_shadow;     // 0: no sphere can report rayFrac <= 1 for any shadow ray of this frame
+    int32_t _pad;
 };
 
 struct DevFrame {
@@ -117,8 +118,7 @@ struct DevFrame {
     // band_index + j * band_count, rows start_row + band * band_height ...; an unbanded frame is
     // one band of end_row - start_row + 1 rows
     int32_t band_height, band_count, band_index, tiles_per_band;
-    int32_t filter_mode;        // 0: FP32 filter + exact fallback (default); 1: exact only;
-                                // 2: verify (run both on every shadow ray, count contradictions)
+    int32_t filter_mode;        // SOFTRAY_FILTER_*: 0 filter + exact fallback, 1 exact only, 2 verify
     int32_t _pad;
 };
 

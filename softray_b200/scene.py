@@ -144,6 +144,7 @@ class FrameParams:
     band_height: int = 0  # row-band partition (one band set per GPU); 0 / band_count<=1 = all rows
     band_count: int = 1
     band_index: int = 0
+    filter_mode: int = 0  # abi.FILTER_AUTO / FILTER_OFF / FILTER_VERIFY (results identical in every mode)
 
     def default_light(self):
         inv = 1.0 / math.sqrt((-1.0) * (-1.0) + (-1.0) * (-1.0) + 1.0 * 1.0)  # Vector.Normalise
@@ -189,5 +190,6 @@ class FrameParams:
         f.band_height = self.band_height
         f.band_count = self.band_count
         f.band_index = self.band_index
+        f.filter_mode = self.filter_mode
         f._keepalive = inst
         return f
