@@ -188,6 +188,8 @@ typedef struct softray_stats {
     uint64_t filter_tests;     /* FP32 filter primitive tests (not part of prim_tests)             */
     uint64_t filter_unsure;    /* rays the filter could not decide (answered in FP64 instead)      */
     uint64_t filter_mismatch;  /* SOFTRAY_FILTER_VERIFY: sure filter answers the FP64 path contradicts */
+    uint64_t rays_bundled;     /* of rays_shadow: answered together, one conservative cone test per
+                                  shading point proving that no triangle can occlude any of its rays */
     double   ms_kernel;        /* CUDA-event time of the render kernel(s)                          */
     double   ms_h2d;           /* frame constants upload                                           */
     double   ms_d2h;           /* framebuffer (+hit ids) readback                                  */

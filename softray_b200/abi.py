@@ -132,6 +132,7 @@ class Stats(C.Structure):
         ("filter_tests", C.c_uint64),
         ("filter_unsure", C.c_uint64),
         ("filter_mismatch", C.c_uint64),
+        ("rays_bundled", C.c_uint64),
         ("ms_kernel", C.c_double),
         ("ms_h2d", C.c_double),
         ("ms_d2h", C.c_double),
@@ -146,7 +147,7 @@ class Stats(C.Structure):
         return self.rays_primary + self.rays_shadow + self.rays_secondary
 
 
-EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 192, "stats": 128}
+EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 192, "stats": 136}
 
 assert C.sizeof(Mesh) == EXPECTED_SIZES["mesh"]
 assert C.sizeof(Sphere) == EXPECTED_SIZES["sphere"]

@@ -309,6 +309,16 @@ inline double max_abs3(const double* a, const double* b)
 // fma(plane, 1/d, -o/d) with o, d and the box planes rounded to FP32; all those roundings together
 // move a box face by < 4e-7 * (largest coordinate in play).  Boxes are padded by 2^-18 of that
 // (~9.5x margin) so the test can only produce false positives.
+// SAH primitive-test costs relative to one node visit (measured instruction counts);
+// SOFTRAY_SAH_ISECT overrides both for experiments.
+constexpr double kTriIsectCost = 2.0, kSphereIsectCost = 2.0;
+inline double sah_isect_cost(double dflt)
+{
+    const char* e = std::getenv("SOFTRAY_SAH_ISECT");
+    if (e && *e) { const double v = std::atof(e); if (v > 0.0) return v; }
+    return dflt;
+}
+
 inline float traversal_pad(double max_coord) { return round_up(std::ldexp(std::fmax(max_coord, 1e-30), -18)); }
 
 }  // namespace
@@ -447,7 +457,7 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
             if (rc != SOFTRAY_OK) return rc;
         } else {
             BvhBuild bvh;
-            build_bvh(bounds, traversal_pad(max_abs3(m.bbox_min, m.bbox_max)), kMaxLeafPrims, &bvh);
+            build_bvh(bounds, traversal_pad(max_abs3(m.bbox_min, m.bbox_max)), kMaxLeafPrims, sah_isect_cost(kTriIsectCost), &bvh);
             if (bvh.depth >= kStackEntries) return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_scene_create: BVH too deep");
             std::vector<TriRec> ordered((size_t)m.n_tris);
             for (int32_t k = 0; k < m.n_tris; k++) ordered[(size_t)k] = recs[(size_t)bvh.order[(size_t)k]];
@@ -498,7 +508,7 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
         } else {
             BvhBuild bvh;
             const float pad = traversal_pad(max_abs3(lo, hi));
-            build_bvh(bounds, pad, kMaxLeafPrims, &bvh);
+            build_bvh(bounds, pad, kMaxLeafPrims, sah_isect_cost(kSphereIsectCost), &bvh);
             if (bvh.depth >= kStackEntries) return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_scene_create: BVH too deep");
             std::vector<SphereRec> ordered((size_t)desc->n_spheres);
             for (int32_t k = 0; k < desc->n_spheres; k++) ordered[(size_t)k] = recs[(size_t)bvh.order[(size_t)k]];
@@ -662,6 +672,14 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
         area_light_offsets(fr->random_seed, f.shadow_samples, ctx->h_offsets);
         ctx->cached_samples = f.shadow_samples; ctx->cached_seed = fr->random_seed;
     }
+    if (f.shadows) {
+        double r2 = 0.0;
+        for (int i = 0; i < f.shadow_samples; i++) {
+            const double* o = ctx->h_offsets + 3 * i;
+            r2 = std::fmax(r2, o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+        }
+        f.light_radius = round_up(std::sqrt(r2) * (1.0 + 1e-6));
+    }
 
     int32_t base = 0;
     for (int32_t i = 0; i < fr->n_instances; i++) {
@@ -737,6 +755,7 @@ int collect_stats(softray_ctx* ctx, cudaStream_t stream, softray_stats* st, bool
     st->node_visits = c.node_visits; st->prim_tests = c.prim_tests; st->sphere_tests = c.sphere_tests;
     st->hits_primary = c.hits_primary; st->shaded_hits = c.shaded_hits;
     st->filter_tests = c.filter_tests; st->filter_unsure = c.filter_unsure; st->filter_mismatch = c.filter_mismatch;
+    st->rays_bundled = c.rays_bundled;
     st->launches = 1;
     float ms = 0.f;
     SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); st->ms_h2d = ms;

@@ -56,9 +56,10 @@ struct Builder {
     BvhBuild* out;
     float pad;
     int max_leaf;
+    double isect_cost;   // SAH cost of one primitive test in units of one node visit
 
-    Builder(const std::vector<PrimBounds>& p, float pad_, int max_leaf_, BvhBuild* o)
-        : prims(p), out(o), pad(pad_), max_leaf(max_leaf_)
+    Builder(const std::vector<PrimBounds>& p, float pad_, int max_leaf_, double isect_cost_, BvhBuild* o)
+        : prims(p), out(o), pad(pad_), max_leaf(max_leaf_), isect_cost(isect_cost_)
     {
     }
 
@@ -67,6 +68,14 @@ struct Builder {
         int32_t count;   // 0 internal, >0 leaf, -1 none
         Box box;
     };
+
+    // traversal link (sr_types.h BvhNode): internal child = node index, leaf = -1 - (first * 16 + count),
+    // no child = kNoChild (an empty leaf behind an unreachable box)
+    static int32_t encode(const Child& c)
+    {
+        if (c.count < 0) return kNoChild;
+        return c.count == 0 ? c.ref : -1 - (c.ref * 16 + c.count);
+    }
 
     void write_box(float* lo3, float* hi3, const Box& b) const
     {
@@ -81,13 +90,13 @@ struct Builder {
         BvhNode& n = out->nodes[(size_t)node];
         float lo[3], hi[3];
         if (a.count >= 0) write_box(lo, hi, a.box);
-        else { lo[0] = lo[1] = lo[2] = FLT_MAX; hi[0] = hi[1] = hi[2] = -FLT_MAX; }
+        else { lo[0] = lo[1] = lo[2] = FLT_MAX; hi[0] = hi[1] = hi[2] = FLT_MAX; }
         n.lo0x = lo[0]; n.lo0y = lo[1]; n.lo0z = lo[2]; n.hi0x = hi[0]; n.hi0y = hi[1]; n.hi0z = hi[2];
         if (b.count >= 0) write_box(lo, hi, b.box);
-        else { lo[0] = lo[1] = lo[2] = FLT_MAX; hi[0] = hi[1] = hi[2] = -FLT_MAX; }
+        else { lo[0] = lo[1] = lo[2] = FLT_MAX; hi[0] = hi[1] = hi[2] = FLT_MAX; }
         n.lo1x = lo[0]; n.lo1y = lo[1]; n.lo1z = lo[2]; n.hi1x = hi[0]; n.hi1y = hi[1]; n.hi1z = hi[2];
-        n.child0 = a.ref; n.count0 = a.count;
-        n.child1 = b.ref; n.count1 = b.count;
+        n.child0 = encode(a); n.count0 = a.count;
+        n.child1 = encode(b); n.count1 = b.count;
     }
 
     Box bounds_of(int32_t begin, int32_t end) const
@@ -140,9 +149,9 @@ struct Builder {
             }
         }
         if (best_axis >= 0) {
-            // leaf cost n * C_isect vs split cost C_trav + cost/area (C_isect = 2, C_trav = 1)
-            const double split_cost = 1.0 + 2.0 * best_cost / parent_area;
-            if (n <= max_leaf && 2.0 * n <= split_cost) return -1;
+            // leaf cost n * C_isect vs split cost C_trav + C_isect * cost/area (C_trav = 1)
+            const double split_cost = 1.0 + isect_cost * best_cost / parent_area;
+            if (n <= max_leaf && isect_cost * n <= split_cost) return -1;
             const float c0 = cb.lo[best_axis], c1 = cb.hi[best_axis];
             const double scale = (double)kBins / ((double)c1 - (double)c0);
             // stable partition keeps the input order inside each side (deterministic layout)
@@ -227,11 +236,11 @@ struct Builder {
 
 }  // namespace
 
-void build_bvh(const std::vector<PrimBounds>& prims, float pad, int max_leaf, BvhBuild* out)
+void build_bvh(const std::vector<PrimBounds>& prims, float pad, int max_leaf, double isect_cost, BvhBuild* out)
 {
     if (max_leaf > kMaxLeafPrims) max_leaf = kMaxLeafPrims;
     if (max_leaf < 1) max_leaf = 1;
-    Builder b(prims, pad, max_leaf, out);
+    Builder b(prims, pad, max_leaf, isect_cost, out);
     b.run();
     if (out->order.empty() && !prims.empty()) out->order = b.idx;
 }

@@ -28,6 +28,7 @@ float round_down(double x);
 float round_up(double x);
 
 // pad: absolute slack added to every node box (space units), see DESIGN.md "FP32 traversal".
-void build_bvh(const std::vector<PrimBounds>& prims, float pad, int max_leaf, BvhBuild* out);
+// isect_cost: SAH cost of one primitive test relative to one node visit (two box tests + stack work).
+void build_bvh(const std::vector<PrimBounds>& prims, float pad, int max_leaf, double isect_cost, BvhBuild* out);
 
 }  // namespace sr

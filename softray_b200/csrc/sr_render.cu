@@ -89,7 +89,7 @@ __device__ __forceinline__ uint32_t mirror_blend(uint32_t local, uint32_t refl)
     return 0xff000000u | (r << 16) | (g << 8) | b;
 }
 
-struct Counters { unsigned int node_visits, prim_tests, sphere_tests, shaded, filter_tests, filter_unsure, filter_mismatch; };
+struct Counters { unsigned int node_visits, prim_tests, sphere_tests, shaded, filter_tests, filter_unsure, filter_mismatch, bundled; };
 
 // ---------------------------------------------------------------------------------------------
 // exact primitive tests
@@ -248,8 +248,9 @@ __device__ __forceinline__ bool slab(const TravRay& r, float lox, float loy, flo
     float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
     float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tcull));
     *t_entry = tmin;
-    // slack for the rounding of the six FMAs (the boxes themselves are padded in space)
-    return tmin <= tmax * 1.00001f + 1e-6f;
+    // no slack here: the boxes are padded in space by 64u x scale (sr_bvh.cpp), > 4x what the roundings
+    // of o, 1/d, the planes and the six FMAs can move a crossing (DESIGN.md "FP32 candidate search")
+    return tmin <= tmax;
 }
 
 // limit in exact-parameter units -> conservative FP32 cull distance measured from the traversal origin
@@ -280,10 +281,9 @@ __device__ __forceinline__ bool walk(const BvhNode* __restrict__ nodes, const vo
             const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
             c->node_visits++;
             float t0, t1;
-            const bool h0 = d.z >= 0 && slab(tr, a.x, a.y, a.z, a.w, b.x, b.y, tcull, &t0);
-            const bool h1 = d.w >= 0 && slab(tr, b.z, b.w, cc.x, cc.y, cc.z, cc.w, tcull, &t1);
-            const int e0 = d.z > 0 ? -1 - (d.x * 16 + d.z) : d.x;
-            const int e1 = d.w > 0 ? -1 - (d.y * 16 + d.w) : d.y;
+            const bool h0 = slab(tr, a.x, a.y, a.z, a.w, b.x, b.y, tcull, &t0);
+            const bool h1 = slab(tr, b.z, b.w, cc.x, cc.y, cc.z, cc.w, tcull, &t1);
+            const int e0 = d.x, e1 = d.y;
             if (h0 && h1) {
                 const bool first0 = t0 <= t1;
                 stack[sp++] = first0 ? e1 : e0;
@@ -439,7 +439,7 @@ __device__ __forceinline__ bool fslab(const FRay& r, float lox, float loy, float
     const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
     const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), r.tcull));
     *t_entry = tmin;
-    return tmin <= tmax * 1.00001f + 1e-6f;      // same slack as slab(): the boxes are padded in space
+    return tmin <= tmax;                         // like slab(): the boxes are padded in space
 }
 
 // 0 surely missed (or outside [0, tmax]), 1 surely hit inside (0, tmax), 2 cannot tell
@@ -491,10 +491,9 @@ __device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes
             const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
             c->node_visits++;
             float t0, t1;
-            const bool h0 = d.z >= 0 && fslab(r, a.x, a.y, a.z, a.w, b.x, b.y, &t0);
-            const bool h1 = d.w >= 0 && fslab(r, b.z, b.w, cc.x, cc.y, cc.z, cc.w, &t1);
-            const int e0 = d.z > 0 ? -1 - (d.x * 16 + d.z) : d.x;
-            const int e1 = d.w > 0 ? -1 - (d.y * 16 + d.w) : d.y;
+            const bool h0 = fslab(r, a.x, a.y, a.z, a.w, b.x, b.y, &t0);
+            const bool h1 = fslab(r, b.z, b.w, cc.x, cc.y, cc.z, cc.w, &t1);
+            const int e0 = d.x, e1 = d.y;
             if (h0 && h1) {
                 const bool first0 = t0 <= t1;
                 stack[sp++] = first0 ? e1 : e0;
@@ -516,6 +515,130 @@ __device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes
         cur = stack[--sp];
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shadow bundles (DESIGN.md "Shadow bundles").  The softShadowQuality rays of one shading point all
+// end in the same point `end` and start inside the ball of radius rho around the light: they lie in
+// the cone  { end + tau * g : 0 <= tau <= 1, |g - g_c| <= rho },  g_c = light - end.  One conservative
+// walk of that cone through the BVH tries to PROVE that every triangle is missed by every ray of the
+// cone in the reference arithmetic; if it succeeds all rays escape and none has to be traced.
+// Per triangle, any one of these suffices (bounds as in tri_filter; spread = rho |n|):
+//   R1  g_c.n + spread < -E          every ray is back-facing (Plane.cs:75)
+//   R2  d - end.n < -E               the plane lies beyond `end`: rayFrac > 1 for every ray
+//   R4  tau1 > 1                     every ray meets the plane before its start
+//   R3  every plane hit P(g) lies within Rp = rho tau2 + |g_c| (tau2 - tau1) of the axis hit P_c, and
+//       s(P_c), u(P_c) are outside the triangle by more than a1 Rp, b1 Rp   (s, u are linear in P)
+//   where [tau1, tau2] bounds num / (g.n) over the cone.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cone_slab(const FRay& r, float rho, float lox, float loy, float loz, float hix, float hiy,
+                                          float hiz)
+{
+    // pass 1: a point of the cone inside the box has tau <= 1, so its axis point lies in the box grown
+    // by rho (L-inf ball contains the L2 ball); pass 2: it then has tau <= tmax1, so grow by rho*tmax1 only
+    float e = rho * r.tcull;
+    float tmax1;
+    {
+        const float ax = __fmaf_rn(lox - e, r.ix, r.nox), bx = __fmaf_rn(hix + e, r.ix, r.nox);
+        const float ay = __fmaf_rn(loy - e, r.iy, r.noy), by = __fmaf_rn(hiy + e, r.iy, r.noy);
+        const float az = __fmaf_rn(loz - e, r.iz, r.noz), bz = __fmaf_rn(hiz + e, r.iz, r.noz);
+        const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+        tmax1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), r.tcull));
+        if (!(tmin <= tmax1)) return false;
+    }
+    e = rho * tmax1 * 1.00001f;
+    const float ax = __fmaf_rn(lox - e, r.ix, r.nox), bx = __fmaf_rn(hix + e, r.ix, r.nox);
+    const float ay = __fmaf_rn(loy - e, r.iy, r.noy), by = __fmaf_rn(hiy + e, r.iy, r.noy);
+    const float az = __fmaf_rn(loz - e, r.iz, r.noz), bz = __fmaf_rn(hiz + e, r.iz, r.noz);
+    const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), r.tcull));
+    return tmin <= tmax;
+}
+
+// true: every ray of the cone surely misses this triangle (in the reference arithmetic)
+__device__ __forceinline__ bool tri_cone_reject(const TriFilt* __restrict__ t, const FRay& r, float rho, float glen, float V)
+{
+    const float4* p = reinterpret_cast<const float4*>(t);
+    const float4 q0 = __ldg(p);
+    const float gn = __fmaf_rn(r.gz, q0.z, __fmaf_rn(r.gy, q0.y, r.gx * q0.x));
+    const float e_gn = (8.0f * kU) * r.g1;
+    const float spread = rho * (1.0f + 4.0f * kU);                     // |n| <= 1 + u
+    if (gn + spread < -e_gn) return true;                              // R1
+    const float num = __fmaf_rn(-r.oz, q0.z, __fmaf_rn(-r.oy, q0.y, __fmaf_rn(-r.ox, q0.x, q0.w)));
+    const float e_num = (8.0f * kU) * (fabsf(q0.w) + r.o1);
+    if (num < -e_num) return true;                                     // R2
+    const float4 q1 = __ldg(p + 1);
+    if (q1.w < 0.0f) return true;                                      // zero-area triangle: never hit
+    const float gn_min = gn - spread - e_gn, gn_max = gn + spread + e_gn;
+    if (!(gn_min > 16.0f * e_gn) || !(gn_min > 0.05f * gn_max)) return false;   // some rays graze the plane
+    const float num_lo = fmaxf(num - e_num, 0.0f), num_hi = num + e_num;
+    const float tau1 = __fdividef(num_lo, gn_max) * (1.0f - 8.0f * kU);
+    const float tau2 = __fdividef(num_hi, gn_min) * (1.0f + 8.0f * kU);
+    if (tau1 > r.tmax_hi) return true;                                 // R4
+    // R3 around the axis hit
+    const float rg = __fdividef(1.0f, gn);
+    const float tau = num * rg;
+    const float e_tau = (e_num + fabsf(tau) * e_gn) * rg * 1.1f + (4.0f * kU) * fabsf(tau);
+    const float4 q3 = __ldg(p + 3);
+    const float wx = __fmaf_rn(r.gx, tau, r.ox) - q3.x, wy = __fmaf_rn(r.gy, tau, r.oy) - q3.y,
+                wz = __fmaf_rn(r.gz, tau, r.oz) - q3.z;
+    const float k = r.ginf * e_tau + (12.0f * kU) * (r.oinf + r.ginf * fabsf(tau) + V);
+    const float rp = (rho * tau2 + glen * (fmaxf(tau2, tau) - fminf(tau1, tau))) * 1.0001f + k;
+    const float sN = __fmaf_rn(wz, q1.z, __fmaf_rn(wy, q1.y, wx * q1.x));
+    const float m_s = q1.w * rp;
+    if (sN < -m_s || sN > 1.0f + m_s) return true;
+    const float4 q2 = __ldg(p + 2);
+    const float uu = __fmaf_rn(wz, q2.z, __fmaf_rn(wy, q2.y, wx * q2.x));
+    const float m_u = q2.w * rp;
+    if (uu < -m_u) return true;
+    if (sN + uu > 1.0f + m_s + m_u + 4.0f * kU) return true;
+    return false;
+}
+
+// true: proven that no ray from the ball (light, rho) to `end` hits any triangle of the mesh
+__device__ __forceinline__ bool bundle_clear(const DevMesh& m, d3 end, d3 light, float rho, Counters* c)
+{
+    FRay r;
+    r.ox = __double2float_rn(end.x); r.oy = __double2float_rn(end.y); r.oz = __double2float_rn(end.z);
+    r.gx = __double2float_rn(light.x - end.x); r.gy = __double2float_rn(light.y - end.y); r.gz = __double2float_rn(light.z - end.z);
+    const float agx = fabsf(r.gx), agy = fabsf(r.gy), agz = fabsf(r.gz);
+    const float aox = fabsf(r.ox), aoy = fabsf(r.oy), aoz = fabsf(r.oz);
+    r.g1 = agx + agy + agz; r.ginf = fmaxf(agx, fmaxf(agy, agz));
+    r.o1 = aox + aoy + aoz; r.oinf = fmaxf(aox, fmaxf(aoy, aoz));
+    if (!(fminf(agx, fminf(agy, agz)) > 1e-30f) || !(r.ginf < 1e30f) || !(r.oinf <= 2.0f * m.scale)) return false;
+    r.ix = __fdiv_rn(1.0f, r.gx); r.iy = __fdiv_rn(1.0f, r.gy); r.iz = __fdiv_rn(1.0f, r.gz);
+    r.nox = -r.ox * r.ix; r.noy = -r.oy * r.iy; r.noz = -r.oz * r.iz;
+    r.tmax_hi = 1.0f; r.tmax_lo = 1.0f; r.tcull = 1.00002f;
+    // the centre g_c itself is rounded: widen the ball by that much
+    const float rho_w = rho + (4.0f * kU) * r.ginf;
+    const float glen = sqrtf(r.gx * r.gx + r.gy * r.gy + r.gz * r.gz) * (1.0f + 8.0f * kU);
+    const BvhNode* __restrict__ nodes = m.nodes;
+    int stack[kStackEntries];
+    int sp = 0;
+    int cur = 0;
+    for (;;) {
+        if (cur >= 0) {
+            const float4* p = reinterpret_cast<const float4*>(nodes + cur);
+            const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
+            c->node_visits++;
+            const bool h0 = cone_slab(r, rho_w, a.x, a.y, a.z, a.w, b.x, b.y);
+            const bool h1 = cone_slab(r, rho_w, b.z, b.w, cc.x, cc.y, cc.z, cc.w);
+            if (h0 && h1) { stack[sp++] = d.y; cur = d.x; continue; }
+            if (h0) { cur = d.x; continue; }
+            if (h1) { cur = d.y; continue; }
+        } else {
+            const int code = -1 - cur;
+            const int first = code >> 4, count = code & 15;
+            for (int i = 0; i < count; i++) {
+                c->filter_tests++;
+                if (!tri_cone_reject(m.filt + first + i, r, rho_w, glen, m.scale)) return false;
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -699,6 +822,14 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
         const int n = f.shadow_samples;
         const bool use_filter = f.filter_mode != 1 && m.nodes != nullptr && m.n_tris > 0;
         *n_shadow += (unsigned int)n;
+        const d3 light = mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]);
+        bool all_clear = false;
+        if (use_filter && f.point_lighting && !in.sph_can_shadow) {
+            all_clear = bundle_clear(m, end, light, f.light_radius, c);
+            if (all_clear) c->bundled += (unsigned int)n;
+        }
+        if (all_clear && f.filter_mode != 2) escaped = n;
+        else
         // 32 samples at a time: the filter answers most rays; the undecided ones are collected in a
         // bit mask and answered by the exact path afterwards, when the lanes of the warp that have
         // any can run it together
@@ -716,7 +847,7 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
                     if (res == 1) res = walk_filter_any(m.nodes, m.filt, r, m.scale, c);
                     if (f.filter_mode == 2) {
                         const bool occ = occluded_mesh(m, f.subdivision, start, dir, c);
-                        if ((res == 0 && occ) || (res == 1 && !occ)) c->filter_mismatch++;
+                        if ((res == 0 && occ) || (res == 1 && !occ) || (all_clear && occ)) c->filter_mismatch++;
                         if (res == 2) c->filter_unsure++;
                         res = occ ? 1 : 0;
                     }
@@ -819,7 +950,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     const int W = f.width, H = f.height, n = f.sub_pixel_res;
     const int n_tiles = f.tiles_x * f.tiles_y;
     Counters c; c.node_visits = 0; c.prim_tests = 0; c.sphere_tests = 0; c.shaded = 0;
-    c.filter_tests = 0; c.filter_unsure = 0; c.filter_mismatch = 0;
+    c.filter_tests = 0; c.filter_unsure = 0; c.filter_mismatch = 0; c.bundled = 0;
     unsigned int n_primary = 0, n_shadow = 0, n_secondary = 0, n_hits = 0;
 
     for (;;) {
@@ -889,10 +1020,10 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     }
 
     // one atomic per warp per counter
-    unsigned long long v[11] = {n_primary, n_shadow, n_secondary, c.node_visits, c.prim_tests, c.sphere_tests, n_hits, c.shaded,
-                                c.filter_tests, c.filter_unsure, c.filter_mismatch};
+    unsigned long long v[12] = {n_primary, n_shadow, n_secondary, c.node_visits, c.prim_tests, c.sphere_tests, n_hits, c.shaded,
+                                c.filter_tests, c.filter_unsure, c.filter_mismatch, c.bundled};
 #pragma unroll
-    for (int k = 0; k < 11; k++) {
+    for (int k = 0; k < 12; k++) {
         unsigned long long x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + k, x);

@@ -62,11 +62,12 @@ struct SR_ALIGN(16) BvhNode {
     float lo0x, lo0y, lo0z, hi0x;
     float hi0y, hi0z, lo1x, lo1y;
     float lo1z, hi1x, hi1y, hi1z;
-    int32_t child0, child1;     // count==0: index of the child node; count>0: first primitive
-    int32_t count0, count1;     // primitives in the child leaf (0 = internal child, -1 = no child)
+    int32_t child0, child1;     // traversal links: >= 0 node index; < 0 leaf -1 - (first * 16 + count); kNoChild
+    int32_t count0, count1;     // primitives in the child leaf (0 = internal child, -1 = no child); host bookkeeping
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
+constexpr int32_t kNoChild = -1;    // = a leaf of zero primitives; its box is the point (+FLT_MAX)^3, which no slab test enters
 constexpr int kMaxLeafPrims = 15;        // fits the 4-bit count of a packed stack entry
 constexpr int kMaxBvhDepth  = 60;        // builder falls back to median splits to stay below this
 constexpr int kStackEntries = 64;
@@ -119,12 +120,12 @@ struct DevFrame {
     // one band of end_row - start_row + 1 rows
     int32_t band_height, band_count, band_index, tiles_per_band;
     int32_t filter_mode;        // SOFTRAY_FILTER_*: 0 filter + exact fallback, 1 exact only, 2 verify
-    int32_t _pad;
+    float   light_radius;       // >= the length of every area-light offset (0.2, ShadowMethod.cs:10), rounded up
 };
 
 struct DevCounters {            // summed over the launch with one atomic per warp per counter
     unsigned long long rays_primary, rays_shadow, rays_secondary, node_visits, prim_tests,
-        sphere_tests, hits_primary, shaded_hits, filter_tests, filter_unsure, filter_mismatch, _pad;
+        sphere_tests, hits_primary, shaded_hits, filter_tests, filter_unsure, filter_mismatch, rays_bundled;
 };
 
 }  // namespace sr

@@ -128,3 +128,15 @@ def test_random_soups(lib, ctx):
         p = scenario(resolution=96, shadows=True, shadow_samples=16, yaw_deg=360.0 * u[0], pitch_deg=60.0 * u[1] - 30.0,
                      object_depth=1.0 + u[2])
         three_ways(sc, p, max_unsure_frac=0.1)
+
+
+def test_bundles_resolve_unoccluded_shading_points(lib, ctx):
+    """config2: the light is outside the room, no triangle can occlude -> every shading point's 100 rays
+    are answered by one cone test; with an occluder in the way only part of them are."""
+    meshes, spheres, p = synth.config2(width=160, height=90, shadow_samples=100, n_spheres=1000)
+    auto = three_ways(lib.Scene(ctx, meshes, spheres), p, max_unsure_frac=0.001)
+    assert auto["stats"].rays_bundled == auto["stats"].rays_shadow
+    mesh = synth.height_field(61, 41)
+    p = scenario(resolution=96, shadows=True, shadow_samples=32, object_depth=1.3)
+    auto = three_ways(lib.Scene(ctx, [mesh]), p)
+    assert 0 < auto["stats"].rays_bundled <= auto["stats"].rays_shadow
