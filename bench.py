@@ -258,7 +258,8 @@ def main():
     # counters of this rank's share (one stats-enabled frame, also a first warm-up)
     st = scene.render_device(frame, target_ptr, stream=stream.cuda_stream, want_stats=True, c_frame=c_frame)
     counters = {k: getattr(st, k) for k in ("rays_primary", "rays_shadow", "rays_secondary", "node_visits", "prim_tests",
-                                            "sphere_tests", "hits_primary", "shaded_hits")}
+                                            "sphere_tests", "hits_primary", "shaded_hits", "filter_tests", "filter_unsure",
+                                            "rays_bundled")}
     if dist is not None:
         t = torch.tensor([counters[k] for k in sorted(counters)], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)

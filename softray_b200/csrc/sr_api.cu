@@ -319,6 +319,13 @@ inline double sah_isect_cost(double dflt)
     return dflt;
 }
 
+constexpr int kBundleMinSamples = 16, kBundleBudget = 192;
+inline int env_int(const char* name, int dflt)
+{
+    const char* e = std::getenv(name);
+    return (e && *e) ? std::atoi(e) : dflt;
+}
+
 inline float traversal_pad(double max_coord) { return round_up(std::ldexp(std::fmax(max_coord, 1e-30), -18)); }
 
 }  // namespace
@@ -679,6 +686,8 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
             r2 = std::fmax(r2, o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
         }
         f.light_radius = round_up(std::sqrt(r2) * (1.0 + 1e-6));
+        // a cone walk pays off when it replaces many rays and stays cheap: bounded to a few single-ray walks
+        f.bundle_budget = f.shadow_samples >= kBundleMinSamples ? env_int("SOFTRAY_BUNDLE_BUDGET", kBundleBudget) : 0;
     }
 
     int32_t base = 0;

@@ -386,6 +386,7 @@ struct FRay {
     float ix, iy, iz;         // 1 / g
     float nox, noy, noz;      // -o / g
     float g1, ginf, o1, oinf; // |g|_1, |g|_inf, |o|_1, |o|_inf
+    float tmin_hi;            // upper bound of the smallest admissible tau (0 for shadow rays)
     float tmax_lo, tmax_hi;   // bracket of the largest admissible tau
     float tcull;              // traversal cull distance (>= tmax_hi, with slack)
 };
@@ -426,6 +427,54 @@ __device__ __forceinline__ int fray_setup(const DevMesh& m, int subdivision, d3 
     // an anchor far from the mesh: the BVH pad (sr_bvh.cpp) assumes an origin within ~2x its scale
     if (!(r->oinf <= 2.0f * m.scale) || !(in_lo == in_lo)) return 2;
     r->tmax_lo = subdivision ? fminf(1.0f, out_lo) : 1.0f;
+    r->tmin_hi = 0.0f;
+    r->tcull = r->tmax_hi * 1.00002f + 1e-6f;
+    return 1;
+}
+
+// Forward (camera / reflection) ray  start + dir * t,  t >= 0.  The FP32 anchor is the point at
+// t0 <= (exact entry into the root box), computed in FP64 and then rounded, so that every FP32 operand
+// is of the order of the mesh whatever the distance of the camera; tau = t - t0.
+// 0: the ray surely misses the root box (no hit), 1: traverse, 2: cannot tell.
+__device__ __forceinline__ int fray_setup_fwd(const DevMesh& m, int subdivision, d3 s, d3 dir, FRay* r, double* t0_out)
+{
+    const float sx = __double2float_rn(s.x), sy = __double2float_rn(s.y), sz = __double2float_rn(s.z);
+    r->gx = __double2float_rn(dir.x); r->gy = __double2float_rn(dir.y); r->gz = __double2float_rn(dir.z);
+    const float agx = fabsf(r->gx), agy = fabsf(r->gy), agz = fabsf(r->gz);
+    const float asx = fabsf(sx), asy = fabsf(sy), asz = fabsf(sz);
+    r->g1 = agx + agy + agz; r->ginf = fmaxf(agx, fmaxf(agy, agz));
+    if (!(fminf(agx, fminf(agy, agz)) > 1e-30f) || !(r->ginf < 1e30f) || !(fmaxf(asx, fmaxf(asy, asz)) < 1e30f)) return 2;
+    r->ix = __fdiv_rn(1.0f, r->gx); r->iy = __fdiv_rn(1.0f, r->gy); r->iz = __fdiv_rn(1.0f, r->gz);
+    // crossings of the root box from the (possibly far) start, per-axis bounds as in fray_setup
+    const float fxa = (m.fmin[0] - sx) * r->ix, fxb = (m.fmax[0] - sx) * r->ix;
+    const float fya = (m.fmin[1] - sy) * r->iy, fyb = (m.fmax[1] - sy) * r->iy;
+    const float fza = (m.fmin[2] - sz) * r->iz, fzb = (m.fmax[2] - sz) * r->iz;
+    const float farx = fmaxf(fxa, fxb), fary = fmaxf(fya, fyb), farz = fmaxf(fza, fzb);
+    const float nearx = fminf(fxa, fxb), neary = fminf(fya, fyb), nearz = fminf(fza, fzb);
+    const float px = fabsf(r->ix) * ((2.0f * kU) * (m.scale + asx) + 4e-10f);
+    const float py = fabsf(r->iy) * ((2.0f * kU) * (m.scale + asy) + 4e-10f);
+    const float pz = fabsf(r->iz) * ((2.0f * kU) * (m.scale + asz) + 4e-10f);
+    const float out_hi = fminf(farx + (px + (4.0f * kU) * fabsf(farx)),
+                               fminf(fary + (py + (4.0f * kU) * fabsf(fary)), farz + (pz + (4.0f * kU) * fabsf(farz))));
+    const float in_lo = fmaxf(nearx - (px + (4.0f * kU) * fabsf(nearx)),
+                              fmaxf(neary - (py + (4.0f * kU) * fabsf(neary)), nearz - (pz + (4.0f * kU) * fabsf(nearz))));
+    const float in_hi = fmaxf(nearx + (px + (4.0f * kU) * fabsf(nearx)),
+                              fmaxf(neary + (py + (4.0f * kU) * fabsf(neary)), nearz + (pz + (4.0f * kU) * fabsf(nearz))));
+    if (!(out_hi >= 0.0f)) return out_hi < 0.0f ? 0 : 2;      // the box lies behind the start
+    if (in_lo > out_hi) return 0;                             // the box is missed
+    if (!(in_lo == in_lo) || !(in_hi == in_hi) || !(out_hi < 9000.0f)) return 2;   // (the reference's ray ends at t = 10000)
+    const float t0 = fmaxf(in_lo, 0.0f);
+    *t0_out = (double)t0;
+    const double ax = s.x + dir.x * (double)t0, ay = s.y + dir.y * (double)t0, az = s.z + dir.z * (double)t0;
+    r->ox = __double2float_rn(ax); r->oy = __double2float_rn(ay); r->oz = __double2float_rn(az);
+    const float aox = fabsf(r->ox), aoy = fabsf(r->oy), aoz = fabsf(r->oz);
+    r->o1 = aox + aoy + aoz; r->oinf = fmaxf(aox, fmaxf(aoy, aoz));
+    if (!(r->oinf <= 2.0f * m.scale)) return 2;
+    r->nox = -r->ox * r->ix; r->noy = -r->oy * r->iy; r->noz = -r->oz * r->iz;
+    // the clipped start of SpatialSubdivision.IntersectRay lies at tau in [0, gap]
+    r->tmin_hi = subdivision ? (fmaxf(in_hi, 0.0f) - t0) * (1.0f + 4.0f * kU) + (4.0f * kU) * fabsf(in_hi) : 0.0f;
+    r->tmax_hi = (out_hi - t0) * (1.0f + 4.0f * kU) + (4.0f * kU) * fabsf(out_hi);
+    r->tmax_lo = 1e30f;
     r->tcull = r->tmax_hi * 1.00002f + 1e-6f;
     return 1;
 }
@@ -442,22 +491,30 @@ __device__ __forceinline__ bool fslab(const FRay& r, float lox, float loy, float
     return tmin <= tmax;                         // like slab(): the boxes are padded in space
 }
 
-// 0 surely missed (or outside [0, tmax]), 1 surely hit inside (0, tmax), 2 cannot tell
-__device__ __forceinline__ int tri_filter(const TriFilt* __restrict__ t, const FRay& r, float V)
+// 0 surely missed (or outside the admissible tau range), 1 surely hit inside it, 2 cannot tell.
+// FWD = false: tau runs against the ray (shadow rays, g = -dir); FWD = true: along it (g = dir), which
+// flips the sign of the plane.  thi: candidates surely beyond it are of no interest (-> 0).
+// On 1 and 2, [*tau_o - *etau_o, *tau_o + *etau_o] contains the exact tau (0 +- 0 when not even that is known).
+template <bool FWD>
+__device__ __forceinline__ int tri_filter(const TriFilt* __restrict__ t, const FRay& r, float V, float thi, float* tau_o,
+                                          float* etau_o)
 {
     const float4* p = reinterpret_cast<const float4*>(t);
     const float4 q0 = __ldg(p);                                          // n, d
-    const float gn = __fmaf_rn(r.gz, q0.z, __fmaf_rn(r.gy, q0.y, r.gx * q0.x));
+    float gn = __fmaf_rn(r.gz, q0.z, __fmaf_rn(r.gy, q0.y, r.gx * q0.x));
+    if (FWD) gn = -gn;
     const float e_gn = (8.0f * kU) * r.g1;
+    *tau_o = 0.0f; *etau_o = 0.0f;
     if (!(gn > e_gn)) return gn < -e_gn ? 0 : 2;                         // dir.n >= 0: one-sided (Plane.cs:75)
-    const float num = __fmaf_rn(-r.oz, q0.z, __fmaf_rn(-r.oy, q0.y, __fmaf_rn(-r.ox, q0.x, q0.w)));
+    float num = __fmaf_rn(-r.oz, q0.z, __fmaf_rn(-r.oy, q0.y, __fmaf_rn(-r.ox, q0.x, q0.w)));
+    if (FWD) num = -num;
     const float e_num = (8.0f * kU) * (fabsf(q0.w) + r.o1);
-    if (num < -e_num) return 0;                                          // tau < 0: rayFrac > 1
+    if (num < -e_num) return 0;                                          // tau < 0
     if (!(gn > 16.0f * e_gn)) return 2;                                  // grazing: tau not trustworthy
     const float rg = __fdividef(1.0f, gn);
     const float tau = num * rg;
     const float e_tau = (e_num + fabsf(tau) * e_gn) * rg * 1.1f + (4.0f * kU) * fabsf(tau);
-    if (tau - e_tau > r.tmax_hi) return 0;                               // before the (clipped) start
+    if (tau - e_tau > thi) return 0;
     const float4 q3 = __ldg(p + 3);                                      // v1, -
     const float wx = __fmaf_rn(r.gx, tau, r.ox) - q3.x, wy = __fmaf_rn(r.gy, tau, r.oy) - q3.y,
                 wz = __fmaf_rn(r.gz, tau, r.oz) - q3.z;
@@ -473,7 +530,10 @@ __device__ __forceinline__ int tri_filter(const TriFilt* __restrict__ t, const F
     if (uu < -e_u) return 0;
     const float sum = sN + uu, e_sum = e_s + e_u + 4.0f * kU;
     if (sum > 1.0f + e_sum) return 0;
-    if (num > e_num && tau + e_tau < r.tmax_lo && sN > e_s && uu > e_u && sum < 1.0f - e_sum) return 1;
+    *tau_o = tau; *etau_o = e_tau;
+    if (num > e_num && tau - e_tau > r.tmin_hi && tau + e_tau < r.tmax_lo && sN > e_s && uu > e_u && sum < 1.0f - e_sum)
+        return 1;
+    if (!(e_tau == e_tau) || !(tau == tau)) { *tau_o = 0.0f; *etau_o = 0.0f; }
     return 2;                                                            // also every NaN / inf case
 }
 
@@ -507,7 +567,8 @@ __device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes
             const int first = code >> 4, count = code & 15;
             for (int i = 0; i < count; i++) {
                 c->filter_tests++;
-                const int res = tri_filter(filt + first + i, r, V);
+                float tau, etau;
+                const int res = tri_filter<false>(filt + first + i, r, V, r.tmax_hi, &tau, &etau);
                 if (res) return res;
             }
         }
@@ -515,6 +576,61 @@ __device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes
         cur = stack[--sp];
     }
     return 0;
+}
+
+// Nearest hit with the filter at the leaves.  Tracks the sure hit with the smallest upper bound
+// (best) and the smallest lower bound of every OTHER candidate, sure or not (other_lo): the winner of
+// the exact arithmetic is known iff best_hi < other_lo.
+struct FClosest { float best_lo, best_hi, other_lo; int best_k; };
+
+__device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, FRay& r,
+                                                    float V, FClosest* out, Counters* c)
+{
+    int stack[kStackEntries];
+    int sp = 0;
+    int cur = 0;
+    float best_lo = 1e30f, best_hi = 1e30f, other_lo = 1e30f;
+    int best_k = -1;
+    for (;;) {
+        if (cur >= 0) {
+            const float4* p = reinterpret_cast<const float4*>(nodes + cur);
+            const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
+            c->node_visits++;
+            float t0, t1;
+            const bool h0 = fslab(r, a.x, a.y, a.z, a.w, b.x, b.y, &t0);
+            const bool h1 = fslab(r, b.z, b.w, cc.x, cc.y, cc.z, cc.w, &t1);
+            const int e0 = d.x, e1 = d.y;
+            if (h0 && h1) {
+                const bool first0 = t0 <= t1;
+                stack[sp++] = first0 ? e1 : e0;
+                cur = first0 ? e0 : e1;
+                continue;
+            }
+            if (h0) { cur = e0; continue; }
+            if (h1) { cur = e1; continue; }
+        } else {
+            const int code = -1 - cur;
+            const int first = code >> 4, count = code & 15;
+            for (int i = 0; i < count; i++) {
+                c->filter_tests++;
+                float tau, etau;
+                const int res = tri_filter<true>(filt + first + i, r, V, best_hi, &tau, &etau);
+                if (res == 0) continue;
+                const float lo = tau - etau, hi = tau + etau;
+                if (res == 1 && hi < best_hi) {
+                    other_lo = fminf(other_lo, best_lo);
+                    best_lo = lo; best_hi = hi; best_k = first + i;
+                    r.tcull = hi * 1.00002f + 1e-6f;
+                } else {
+                    other_lo = fminf(other_lo, lo);
+                }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    out->best_lo = best_lo; out->best_hi = best_hi; out->other_lo = other_lo; out->best_k = best_k;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -596,7 +712,7 @@ __device__ __forceinline__ bool tri_cone_reject(const TriFilt* __restrict__ t, c
 }
 
 // true: proven that no ray from the ball (light, rho) to `end` hits any triangle of the mesh
-__device__ __forceinline__ bool bundle_clear(const DevMesh& m, d3 end, d3 light, float rho, Counters* c)
+__device__ __forceinline__ bool bundle_clear(const DevMesh& m, d3 end, d3 light, float rho, int budget, Counters* c)
 {
     FRay r;
     r.ox = __double2float_rn(end.x); r.oy = __double2float_rn(end.y); r.oz = __double2float_rn(end.z);
@@ -622,6 +738,7 @@ __device__ __forceinline__ bool bundle_clear(const DevMesh& m, d3 end, d3 light,
             const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
             const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
             c->node_visits++;
+            if (--budget < 0) return false;                 // too much geometry near the cone: trace the rays
             const bool h0 = cone_slab(r, rho_w, a.x, a.y, a.z, a.w, b.x, b.y);
             const bool h1 = cone_slab(r, rho_w, b.z, b.w, cc.x, cc.y, cc.z, cc.w);
             if (h0 && h1) { stack[sp++] = d.y; cur = d.x; continue; }
@@ -653,39 +770,87 @@ struct Hit {
 
 constexpr double kNoHit = 1.7976931348623157e308;   // double.MaxValue (GeometryCollection.cs:48)
 
-__device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, d3 s, d3 dir, Hit* h,
-                                         Counters* c)
+// Exact (reference arithmetic) nearest sphere / nearest triangle.
+__device__ __noinline__ void spheres_closest_exact(const DevScene& sc, d3 s, d3 dirn, BestPrim* bs, Counters* c)
+{
+    if (sc.sphere_nodes) {
+        double te;
+        if (entry_clip(sc.sph_bmin, sc.sph_bmax, 0.0, s, dirn, &te)) {
+            const TravRay tr = make_trav(s, dirn, te);
+            walk<1, false>(sc.sphere_nodes, sc.spheres, tr, s, dirn, kNoHit, 0.0, bs, c);
+        }
+    } else {
+        scan<1, false>(sc.spheres, sc.n_spheres, s, dirn, kNoHit, 0.0, bs, c);
+    }
+}
+
+// only_k >= 0: test that one triangle only (the filter has proven it to be the winner)
+__device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivision, d3 s, d3 dir, int only_k, BestPrim* bt,
+                                                d3* ts_out, double* offset_out, Counters* c)
+{
+    d3 ts = s; double offset = 0.0;
+    *ts_out = s; *offset_out = 0.0;
+    if (subdivision && !reference_clip(m.bmin, m.bmax, &ts, dir, &offset)) return;
+    *ts_out = ts; *offset_out = offset;
+    if (only_k >= 0) {
+        double rf;
+        c->prim_tests++;
+        if (tri_intersect(m.tris + only_k, ts, dir, kNoHit, &rf)) {
+            bt->rf = rf; bt->k = only_k; bt->index = __ldg(reinterpret_cast<const int*>(m.tris + only_k) + 31);
+        }
+        return;
+    }
+    if (m.nodes) {
+        double te = 0.0;
+        // the clipped start already lies on/in the root box; otherwise enter it first
+        if (subdivision || entry_clip(m.bmin, m.bmax, 0.0, ts, dir, &te)) {
+            const TravRay tr = make_trav(ts, dir, te);
+            walk<0, false>(m.nodes, m.tris, tr, ts, dir, kNoHit, 0.0, bt, c);
+        }
+    } else {
+        scan<0, false>(m.tris, m.n_tris, ts, dir, kNoHit, 0.0, bt, c);
+    }
+}
+
+// IRayIntersectable.IntersectRay of rootGeometry for a camera / reflection ray: the nearest hit.
+__device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, int filter_mode, d3 s, d3 dir,
+                                            Hit* h, Counters* c)
 {
     // --- spheres (tested first in list order) ---
     BestPrim bs; bs.rf = kNoHit; bs.k = -1; bs.index = 0x7fffffff;
     d3 dirn = dir;
     if (sc.n_spheres > 0) {
         dirn = vnormalise(dir);                          // Sphere.cs:160
-        if (sc.sphere_nodes) {
-            double te;
-            if (entry_clip(sc.sph_bmin, sc.sph_bmax, 0.0, s, dirn, &te)) {
-                const TravRay tr = make_trav(s, dirn, te);
-                walk<1, false>(sc.sphere_nodes, sc.spheres, tr, s, dirn, kNoHit, 0.0, &bs, c);
-            }
-        } else {
-            scan<1, false>(sc.spheres, sc.n_spheres, s, dirn, kNoHit, 0.0, &bs, c);
-        }
+        spheres_closest_exact(sc, s, dirn, &bs, c);
     }
     // --- mesh ---
     BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
-    d3 ts = s; double offset = 0.0; bool in_box = true;
+    d3 ts = s; double offset = 0.0;
     if (m.n_tris > 0) {
-        if (subdivision) in_box = reference_clip(m.bmin, m.bmax, &ts, dir, &offset);
-        if (in_box) {
-            if (m.nodes) {
-                double te = 0.0;
-                // the clipped start already lies on/in the root box; otherwise enter it first
-                if (subdivision || entry_clip(m.bmin, m.bmax, 0.0, ts, dir, &te)) {
-                    const TravRay tr = make_trav(ts, dir, te);
-                    walk<0, false>(m.nodes, m.tris, tr, ts, dir, kNoHit, 0.0, &bt, c);
-                }
-            } else {
-                scan<0, false>(m.tris, m.n_tris, ts, dir, kNoHit, 0.0, &bt, c);
+        int known = 2;                                   // 0: surely no hit, 1: winner = fk, 2: ask the exact path
+        int fk = -1;
+        if (filter_mode != 1 && m.nodes != nullptr) {
+            FRay r; double t0;
+            known = fray_setup_fwd(m, subdivision, s, dir, &r, &t0);
+            if (known == 1) {
+                FClosest fc;
+                walk_filter_closest(m.nodes, m.filt, r, m.scale, &fc, c);
+                if (fc.best_k >= 0 && fc.best_hi < fc.other_lo) fk = fc.best_k;
+                else known = (fc.best_k < 0 && fc.other_lo >= 1e30f) ? 0 : 2;
+            }
+        }
+        if (filter_mode == 2) {
+            mesh_closest_exact(m, subdivision, s, dir, -1, &bt, &ts, &offset, c);
+            if ((known == 0 && bt.k >= 0) || (known == 1 && bt.k != fk)) c->filter_mismatch++;
+            if (known == 2) c->filter_unsure++;
+        } else {
+            if (known == 1) {
+                mesh_closest_exact(m, subdivision, s, dir, fk, &bt, &ts, &offset, c);
+                if (bt.k < 0) known = 2;                 // cannot happen if the bounds hold; stay correct anyway
+            }
+            if (known == 2) {
+                if (filter_mode != 1 && m.nodes != nullptr) c->filter_unsure++;
+                mesh_closest_exact(m, subdivision, s, dir, -1, &bt, &ts, &offset, c);
             }
         }
     }
@@ -824,8 +989,8 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
         *n_shadow += (unsigned int)n;
         const d3 light = mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]);
         bool all_clear = false;
-        if (use_filter && f.point_lighting && !in.sph_can_shadow) {
-            all_clear = bundle_clear(m, end, light, f.light_radius, c);
+        if (use_filter && f.point_lighting && !in.sph_can_shadow && f.bundle_budget > 0) {
+            all_clear = bundle_clear(m, end, light, f.light_radius, f.bundle_budget, c);
             if (all_clear) c->bundled += (unsigned int)n;
         }
         if (all_clear && f.filter_mode != 2) escaped = n;
@@ -885,7 +1050,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
     if (f.n_instances == 1) {
         const DevInstance& in = insts[0];
         dir0 = dirs_are_view ? mul3x3(in.Minv, dirs_view_or_world[0]) : dirs_view_or_world[0];
-        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, starts[0], dir0, &h, c);
+        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, c);
     } else {
         // extension: nearest hit across instances, ties to the lowest instance
         double best = kNoHit;
@@ -893,7 +1058,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
             const DevInstance& in = insts[i];
             const d3 d = mul3x3(in.Minv, dirs_view_or_world[0]);
             Hit hi;
-            if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, mk(in.start[0], in.start[1], in.start[2]), d, &hi, c) &&
+            if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]), d, &hi, c) &&
                 hi.rf < best) {
                 best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
             }
@@ -916,7 +1081,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
             const d3 rs = vadd(h.pos, vscale(h.normal, 0.001));
             (*n_secondary)++;
             Hit h2;
-            if (!closest_hit(sc, m, f.subdivision, rs, r, &h2, c)) { tail = f.background; have_tail = true; break; }
+            if (!closest_hit(sc, m, f.subdivision, f.filter_mode, rs, r, &h2, c)) { tail = f.background; have_tail = true; break; }
             h = h2; d = r;
             local[++depth] = shade_and_shadow(f, sc, in, m, offsets, h, c, n_shadow);
         }

@@ -121,6 +121,8 @@ struct DevFrame {
     int32_t band_height, band_count, band_index, tiles_per_band;
     int32_t filter_mode;        // SOFTRAY_FILTER_*: 0 filter + exact fallback, 1 exact only, 2 verify
     float   light_radius;       // >= the length of every area-light offset (0.2, ShadowMethod.cs:10), rounded up
+    int32_t bundle_budget;      // node visits a shadow-bundle cone walk may spend before giving up (0 = no bundles)
+    int32_t _pad;
 };
 
 struct DevCounters {            // summed over the launch with one atomic per warp per counter

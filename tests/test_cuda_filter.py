@@ -140,3 +140,26 @@ def test_bundles_resolve_unoccluded_shading_points(lib, ctx):
     p = scenario(resolution=96, shadows=True, shadow_samples=32, object_depth=1.3)
     auto = three_ways(lib.Scene(ctx, [mesh]), p)
     assert 0 < auto["stats"].rays_bundled <= auto["stats"].rays_shadow
+
+
+def test_closest_hit_filter_primary_and_reflection(lib, ctx, obj_mesh, obj2_mesh):
+    """Camera and mirror rays: the filter names the winning triangle, the reference arithmetic evaluates
+    only that one (or everything, when the filter cannot separate the candidates)."""
+    for mesh in (obj_mesh, obj2_mesh):
+        sc = lib.Scene(ctx, [mesh])
+        for kw in (dict(), dict(subdivision=False), dict(sub_pixel_res=3, focal_blur=False), dict(sub_pixel_res=2, focal_blur=True),
+                   dict(reflection_depth=2, texture3d_id=1), dict(object_depth=0.3), dict(yaw_deg=0.0, pitch_deg=0.0)):
+            auto = three_ways(sc, scenario(resolution=128, **kw))
+            assert auto["stats"].filter_unsure <= 0.25 * auto["stats"].rays_primary + 50   # (obj2: faces in the root box faces)
+    meshes, _, p = synth.config3(width=200, height=112, nx=301, nz=201, shadow_samples=4)
+    auto = three_ways(lib.Scene(ctx, meshes), p)
+    assert auto["stats"].rays_secondary > 0
+    meshes, _, p = synth.config4(width=160, height=90, n_lon=60, n_lat=40, n_side=4, sub_pixel_res=2)
+    three_ways(lib.Scene(ctx, meshes), p)
+
+
+def test_camera_inside_the_bounding_box(lib, ctx):
+    """A camera inside the room: rays start inside the root box (no clip, SpatialSubdivision.cs:389-398)."""
+    meshes, spheres, p = synth.config2(width=128, height=72, shadow_samples=8, n_spheres=200)
+    p.instances[0].position = (0.0, 0.0, 0.2)
+    three_ways(lib.Scene(ctx, meshes, spheres), p, max_unsure_frac=1.0)
