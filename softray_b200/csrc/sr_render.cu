@@ -89,7 +89,16 @@ __device__ __forceinline__ uint32_t mirror_blend(uint32_t local, uint32_t refl)
     return 0xff000000u | (r << 16) | (g << 8) | b;
 }
 
-struct Counters { unsigned int node_visits, prim_tests, sphere_tests, shaded, filter_tests, filter_unsure, filter_mismatch, bundled; };
+struct Counters {
+    unsigned int node_visits, prim_tests, sphere_tests, shaded, filter_tests, filter_unsure, filter_mismatch, bundled;
+    // shadow-bundle back-off of this lane: after a failed cone walk the next (2^streak - 1) shading points
+    // do not try one (neighbouring shading points mostly fail alike); a success resets it
+    int bundle_skip, bundle_streak;
+};
+// Counters of the out-of-line (exact / per-camera-ray) functions.  These are reached through a pointer,
+// so they live in local memory; each function accumulates in registers and adds once on return.  Keeping
+// them apart leaves the hot shadow-ray counters above in registers.
+struct XCounters { unsigned int node_visits, prim_tests, sphere_tests, filter_tests, filter_unsure, filter_mismatch; };
 
 // ---------------------------------------------------------------------------------------------
 // exact primitive tests
@@ -268,18 +277,20 @@ struct BestPrim { double rf; int k; int index; };
 // lowest list index (GeometryCollection.cs:53, SpatialSubdivision.cs:644).
 template <int PRIM, bool ANY>
 __device__ __forceinline__ bool walk(const BvhNode* __restrict__ nodes, const void* __restrict__ prims, const TravRay& tr,
-                                     d3 s, d3 dir, double limit, double any_offset, BestPrim* best, Counters* c)
+                                     d3 s, d3 dir, double limit, double any_offset, BestPrim* best, XCounters* c)
 {
     int stack[kStackEntries];
     int sp = 0;
     int cur = 0;
+    unsigned int nv = 0, np = 0;
+    bool found = false;
     float tcull = cull_from(ANY ? limit : best->rf, tr.t_off);
     for (;;) {
         if (cur >= 0) {
             const float4* p = reinterpret_cast<const float4*>(nodes + cur);
             const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
             const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
-            c->node_visits++;
+            nv++;
             float t0, t1;
             const bool h0 = slab(tr, a.x, a.y, a.z, a.w, b.x, b.y, tcull, &t0);
             const bool h1 = slab(tr, b.z, b.w, cc.x, cc.y, cc.z, cc.w, tcull, &t1);
@@ -298,12 +309,12 @@ __device__ __forceinline__ bool walk(const BvhNode* __restrict__ nodes, const vo
             for (int i = 0; i < count; i++) {
                 const int k = first + i;
                 double rf;
-                c->prim_tests++;
+                np++;
                 if (PRIM == 0) {
                     const TriRec* t = reinterpret_cast<const TriRec*>(prims) + k;
                     if (!tri_intersect(t, s, dir, ANY ? limit : best->rf, &rf)) continue;
                     if (ANY) {
-                        if (dadd(rf, any_offset) <= 1.0) return true;
+                        if (dadd(rf, any_offset) <= 1.0) { found = true; goto done; }
                         continue;
                     }
                     const int index = __ldg(reinterpret_cast<const int*>(t) + 31);
@@ -313,10 +324,9 @@ __device__ __forceinline__ bool walk(const BvhNode* __restrict__ nodes, const vo
                     }
                 } else {
                     const SphereRec* q = reinterpret_cast<const SphereRec*>(prims) + k;
-                    c->sphere_tests++;
                     if (!sphere_intersect(q, s, dir, &rf)) continue;
                     if (ANY) {
-                        if (rf <= limit) return true;
+                        if (rf <= limit) { found = true; goto done; }
                         continue;
                     }
                     const int index = __ldg(reinterpret_cast<const int*>(q) + 11);
@@ -330,31 +340,37 @@ __device__ __forceinline__ bool walk(const BvhNode* __restrict__ nodes, const vo
         if (sp == 0) break;
         cur = stack[--sp];
     }
-    return false;
+done:
+    c->node_visits += nv; c->prim_tests += np;
+    if (PRIM == 1) c->sphere_tests += np;
+    return found;
 }
 
 // Linear scan (SOFTRAY_ACCEL_BRUTE): GeometryCollection.IntersectRay (GeometryCollection.cs:44-69).
 template <int PRIM, bool ANY>
 __device__ __forceinline__ bool scan(const void* __restrict__ prims, int n, d3 s, d3 dir, double limit, double any_offset,
-                                     BestPrim* best, Counters* c)
+                                     BestPrim* best, XCounters* c)
 {
+    unsigned int np = 0;
+    bool found = false;
     for (int k = 0; k < n; k++) {
         double rf;
-        c->prim_tests++;
+        np++;
         if (PRIM == 0) {
             const TriRec* t = reinterpret_cast<const TriRec*>(prims) + k;
             if (!tri_intersect(t, s, dir, ANY ? limit : best->rf, &rf)) continue;
-            if (ANY) { if (dadd(rf, any_offset) <= 1.0) return true; continue; }
+            if (ANY) { if (dadd(rf, any_offset) <= 1.0) { found = true; break; } continue; }
             if (rf < best->rf) { best->rf = rf; best->k = k; best->index = k; }
         } else {
             const SphereRec* q = reinterpret_cast<const SphereRec*>(prims) + k;
-            c->sphere_tests++;
             if (!sphere_intersect(q, s, dir, &rf)) continue;
-            if (ANY) { if (rf <= limit) return true; continue; }
+            if (ANY) { if (rf <= limit) { found = true; break; } continue; }
             if (rf < best->rf) { best->rf = rf; best->k = k; best->index = k; }
         }
     }
-    return false;
+    c->prim_tests += np;
+    if (PRIM == 1) c->sphere_tests += np;
+    return found;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -584,19 +600,20 @@ __device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes
 struct FClosest { float best_lo, best_hi, other_lo; int best_k; };
 
 __device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, FRay& r,
-                                                    float V, FClosest* out, Counters* c)
+                                                    float V, FClosest* out, XCounters* c)
 {
     int stack[kStackEntries];
     int sp = 0;
     int cur = 0;
     float best_lo = 1e30f, best_hi = 1e30f, other_lo = 1e30f;
     int best_k = -1;
+    unsigned int nv = 0, nf = 0;
     for (;;) {
         if (cur >= 0) {
             const float4* p = reinterpret_cast<const float4*>(nodes + cur);
             const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
             const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
-            c->node_visits++;
+            nv++;
             float t0, t1;
             const bool h0 = fslab(r, a.x, a.y, a.z, a.w, b.x, b.y, &t0);
             const bool h1 = fslab(r, b.z, b.w, cc.x, cc.y, cc.z, cc.w, &t1);
@@ -613,7 +630,7 @@ __device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ 
             const int code = -1 - cur;
             const int first = code >> 4, count = code & 15;
             for (int i = 0; i < count; i++) {
-                c->filter_tests++;
+                nf++;
                 float tau, etau;
                 const int res = tri_filter<true>(filt + first + i, r, V, best_hi, &tau, &etau);
                 if (res == 0) continue;
@@ -630,6 +647,7 @@ __device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ 
         if (sp == 0) break;
         cur = stack[--sp];
     }
+    c->node_visits += nv; c->filter_tests += nf;
     out->best_lo = best_lo; out->best_hi = best_hi; out->other_lo = other_lo; out->best_k = best_k;
 }
 
@@ -771,7 +789,7 @@ struct Hit {
 constexpr double kNoHit = 1.7976931348623157e308;   // double.MaxValue (GeometryCollection.cs:48)
 
 // Exact (reference arithmetic) nearest sphere / nearest triangle.
-__device__ __noinline__ void spheres_closest_exact(const DevScene& sc, d3 s, d3 dirn, BestPrim* bs, Counters* c)
+__device__ __noinline__ void spheres_closest_exact(const DevScene& sc, d3 s, d3 dirn, BestPrim* bs, XCounters* c)
 {
     if (sc.sphere_nodes) {
         double te;
@@ -786,7 +804,7 @@ __device__ __noinline__ void spheres_closest_exact(const DevScene& sc, d3 s, d3 
 
 // only_k >= 0: test that one triangle only (the filter has proven it to be the winner)
 __device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivision, d3 s, d3 dir, int only_k, BestPrim* bt,
-                                                d3* ts_out, double* offset_out, Counters* c)
+                                                d3* ts_out, double* offset_out, XCounters* c)
 {
     d3 ts = s; double offset = 0.0;
     *ts_out = s; *offset_out = 0.0;
@@ -814,7 +832,7 @@ __device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivisio
 
 // IRayIntersectable.IntersectRay of rootGeometry for a camera / reflection ray: the nearest hit.
 __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, int filter_mode, d3 s, d3 dir,
-                                            Hit* h, Counters* c)
+                                            Hit* h, XCounters* c)
 {
     // --- spheres (tested first in list order) ---
     BestPrim bs; bs.rf = kNoHit; bs.k = -1; bs.index = 0x7fffffff;
@@ -881,7 +899,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
 // "shadowInfo != null && shadowInfo.rayFrac <= 1.0" (ShadowMethod.cs:171): true iff ANY primitive
 // reports a rayFrac <= 1.0, because the minimum of the reported rayFracs is what the chain returns.
 // Exact (reference arithmetic) versions, one per primitive kind.
-__device__ __noinline__ bool occluded_mesh(const DevMesh& m, int subdivision, d3 s, d3 dir, Counters* c)
+__device__ __noinline__ bool occluded_mesh(const DevMesh& m, int subdivision, d3 s, d3 dir, XCounters* c)
 {
     BestPrim dummy; dummy.rf = kNoHit; dummy.k = -1; dummy.index = 0;
     if (m.n_tris <= 0) return false;
@@ -901,7 +919,7 @@ __device__ __noinline__ bool occluded_mesh(const DevMesh& m, int subdivision, d3
     return scan<0, true>(m.tris, m.n_tris, ts, dir, limit, offset, &dummy, c);
 }
 
-__device__ __noinline__ bool occluded_spheres(const DevScene& sc, d3 s, d3 dir, Counters* c)
+__device__ __noinline__ bool occluded_spheres(const DevScene& sc, d3 s, d3 dir, XCounters* c)
 {
     BestPrim dummy; dummy.rf = kNoHit; dummy.k = -1; dummy.index = 0;
     if (sc.n_spheres <= 0) return false;
@@ -966,7 +984,7 @@ __device__ __forceinline__ void shadow_ray(const DevFrame& f, const DevInstance&
 }
 
 __device__ __forceinline__ bool occluded_exact(const DevScene& sc, const DevInstance& in, const DevMesh& m, int subdivision,
-                                               d3 start, d3 dir, Counters* c)
+                                               d3 start, d3 dir, XCounters* c)
 {
     if (occluded_mesh(m, subdivision, start, dir, c)) return true;
     return in.sph_can_shadow && occluded_spheres(sc, start, dir, c);
@@ -974,7 +992,7 @@ __device__ __forceinline__ bool occluded_exact(const DevScene& sc, const DevInst
 
 __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const DevScene& sc, const DevInstance& in,
                                                      const DevMesh& m, const double* __restrict__ offsets, const Hit& h,
-                                                     Counters* c, unsigned int* n_shadow)
+                                                     Counters* c, XCounters* xc, unsigned int* n_shadow)
 {
     uint32_t color = h.color;
     c->shaded++;
@@ -990,8 +1008,13 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
         const d3 light = mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]);
         bool all_clear = false;
         if (use_filter && f.point_lighting && !in.sph_can_shadow && f.bundle_budget > 0) {
-            all_clear = bundle_clear(m, end, light, f.light_radius, f.bundle_budget, c);
-            if (all_clear) c->bundled += (unsigned int)n;
+            if (c->bundle_skip > 0) {
+                c->bundle_skip--;
+            } else {
+                all_clear = bundle_clear(m, end, light, f.light_radius, f.bundle_budget, c);
+                if (all_clear) { c->bundled += (unsigned int)n; c->bundle_streak = 0; }
+                else { c->bundle_streak = min(c->bundle_streak + 1, 6); c->bundle_skip = (1 << c->bundle_streak) - 1; }
+            }
         }
         if (all_clear && f.filter_mode != 2) escaped = n;
         else
@@ -1011,12 +1034,12 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
                     int res = fray_setup(m, f.subdivision, anchor, dir, &r);
                     if (res == 1) res = walk_filter_any(m.nodes, m.filt, r, m.scale, c);
                     if (f.filter_mode == 2) {
-                        const bool occ = occluded_mesh(m, f.subdivision, start, dir, c);
+                        const bool occ = occluded_mesh(m, f.subdivision, start, dir, xc);
                         if ((res == 0 && occ) || (res == 1 && !occ) || (all_clear && occ)) c->filter_mismatch++;
                         if (res == 2) c->filter_unsure++;
                         res = occ ? 1 : 0;
                     }
-                    if (res == 0 && in.sph_can_shadow) res = occluded_spheres(sc, start, dir, c) ? 1 : 0;
+                    if (res == 0 && in.sph_can_shadow) res = occluded_spheres(sc, start, dir, xc) ? 1 : 0;
                     if (res == 0) escaped++;
                     else if (res == 2) pending |= 1u << j;
                 }
@@ -1029,7 +1052,7 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
                 d3 start, dir;
                 shadow_ray(f, in, offsets, end, base + j, &start, &dir);
                 if (use_filter) c->filter_unsure++;
-                if (!occluded_exact(sc, in, m, f.subdivision, start, dir, c)) escaped++;
+                if (!occluded_exact(sc, in, m, f.subdivision, start, dir, xc)) escaped++;
             }
         }
         const double frac = ddiv((double)escaped, (double)n);
@@ -1041,7 +1064,7 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
 // TraceRayComplex (Renderer.cs:1850-1879) for one camera ray (+ mirror bounces, + composite instances)
 __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const DevScene& sc, const DevInstance* __restrict__ insts,
                                                      const double* __restrict__ offsets, const d3* starts, const d3* dirs_view_or_world,
-                                                     bool dirs_are_view, Counters* c, unsigned int* n_shadow,
+                                                     bool dirs_are_view, Counters* c, XCounters* xc, unsigned int* n_shadow,
                                                      unsigned int* n_secondary, bool* hit_out)
 {
     PixelOut out; out.color = f.background; out.id = -1;
@@ -1050,7 +1073,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
     if (f.n_instances == 1) {
         const DevInstance& in = insts[0];
         dir0 = dirs_are_view ? mul3x3(in.Minv, dirs_view_or_world[0]) : dirs_view_or_world[0];
-        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, c);
+        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, xc);
     } else {
         // extension: nearest hit across instances, ties to the lowest instance
         double best = kNoHit;
@@ -1058,7 +1081,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
             const DevInstance& in = insts[i];
             const d3 d = mul3x3(in.Minv, dirs_view_or_world[0]);
             Hit hi;
-            if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]), d, &hi, c) &&
+            if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]), d, &hi, xc) &&
                 hi.rf < best) {
                 best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
             }
@@ -1069,22 +1092,24 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
     const DevInstance& in = insts[which];
     const DevMesh& m = sc.meshes[in.mesh];
     out.id = h.id >= 0 ? in.tri_base + h.id : h.id;
+    // local colour of the camera hit, then of up to reflection_depth mirror hits (one call site: the
+    // shading + shadow code is the bulk of the kernel, it must not be instantiated twice)
     uint32_t local[5];
     int depth = 0;
-    local[0] = shade_and_shadow(f, sc, in, m, offsets, h, c, n_shadow);
     uint32_t tail = 0; bool have_tail = false;
-    if (f.reflection_depth > 0 && f.n_instances == 1) {
-        d3 d = dir0;
-        for (int b = 0; b < f.reflection_depth; b++) {
-            // r = d - n * (2 (d.n)), from pos + n*0.001 (PathTracingMethod.cs:10,52)
-            const d3 r = vsub(d, vscale(h.normal, dmul(2.0, vdot(d, h.normal))));
-            const d3 rs = vadd(h.pos, vscale(h.normal, 0.001));
-            (*n_secondary)++;
-            Hit h2;
-            if (!closest_hit(sc, m, f.subdivision, f.filter_mode, rs, r, &h2, c)) { tail = f.background; have_tail = true; break; }
-            h = h2; d = r;
-            local[++depth] = shade_and_shadow(f, sc, in, m, offsets, h, c, n_shadow);
-        }
+    const int bounces = (f.reflection_depth > 0 && f.n_instances == 1) ? f.reflection_depth : 0;
+    d3 d = dir0;
+    for (int b = 0;; b++) {
+        local[depth] = shade_and_shadow(f, sc, in, m, offsets, h, c, xc, n_shadow);
+        if (b >= bounces) break;
+        // r = d - n * (2 (d.n)), from pos + n*0.001 (PathTracingMethod.cs:10,52)
+        const d3 r = vsub(d, vscale(h.normal, dmul(2.0, vdot(d, h.normal))));
+        const d3 rs = vadd(h.pos, vscale(h.normal, 0.001));
+        (*n_secondary)++;
+        Hit h2;
+        if (!closest_hit(sc, m, f.subdivision, f.filter_mode, rs, r, &h2, xc)) { tail = f.background; have_tail = true; break; }
+        h = h2; d = r;
+        depth++;
     }
     uint32_t acc;
     if (have_tail) acc = mirror_blend(local[depth], tail); else acc = local[depth];
@@ -1093,7 +1118,10 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
     return out;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef SR_MIN_BLOCKS
+#define SR_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, SR_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevScene sc, const DevInstance* __restrict__ g_insts, const double* __restrict__ g_offsets,
               uint32_t* __restrict__ pixels, int32_t* __restrict__ hit_ids, unsigned int* __restrict__ tile_counter,
               DevCounters* __restrict__ counters)
@@ -1116,6 +1144,9 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     const int n_tiles = f.tiles_x * f.tiles_y;
     Counters c; c.node_visits = 0; c.prim_tests = 0; c.sphere_tests = 0; c.shaded = 0;
     c.filter_tests = 0; c.filter_unsure = 0; c.filter_mismatch = 0; c.bundled = 0;
+    c.bundle_skip = 0; c.bundle_streak = 0;
+    XCounters xc; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0; xc.filter_unsure = 0;
+    xc.filter_mismatch = 0;
     unsigned int n_primary = 0, n_shadow = 0, n_secondary = 0, n_hits = 0;
 
     for (;;) {
@@ -1130,63 +1161,61 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
         const int row = f.start_row + (f.band_index + band_j * f.band_count) * f.band_height + band_r;
         if (col >= W || band_r >= f.band_height || row > f.end_row) continue;
 
-        PixelOut po; bool hit;
-        if (n == 1) {
-            // Renderer.cs:1728-1729
+        // one loop for 1 spp (Renderer.cs:1722-1743) and n x n sub-pixels (:1744-1826): with n == 1 the
+        // sub-pixel fraction is 0.0 and (col + 0.0) / W is bit-identical to col / W
+        PixelOut po; bool hit = false;
+        po.color = 0; po.id = -1;
+        int sum_r = 0, sum_g = 0, sum_b = 0;
+        const DevInstance& in0 = s_insts[0];
+        const bool focal = f.focal_blur && n > 1;                                         // App. A #11
+        d3 focal_pt = mk(0, 0, 0);
+        if (focal) {
             const d3 dir_view = mk(-dsub(ddiv((double)col, (double)W), 0.5),
                                    dmul(-dsub(ddiv((double)row, (double)H), 0.5), f.aspect), f.fov_depth);
-            const d3 start = mk(s_insts[0].start[0], s_insts[0].start[1], s_insts[0].start[2]);
-            n_primary++;
-            po = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir_view, true, &c, &n_shadow, &n_secondary, &hit);
-            if (hit) n_hits++;
-        } else {
-            int sum_r = 0, sum_g = 0, sum_b = 0;
-            d3 focal_pt = mk(0, 0, 0);
-            const DevInstance& in0 = s_insts[0];
-            if (f.focal_blur) {
-                const d3 dir_view = mk(-dsub(ddiv((double)col, (double)W), 0.5),
-                                       dmul(-dsub(ddiv((double)row, (double)H), 0.5), f.aspect), f.fov_depth);
-                const d3 dw = mul3x3(in0.Minv, dir_view);
-                focal_pt = vadd(vscale(dw, f.focal_depth), mk(in0.start[0], in0.start[1], in0.start[2]));   // :1759
-            }
-            po.color = 0; po.id = -1; hit = false;
-            for (int sx = 0; sx < n; sx++) {
-                for (int sy = 0; sy < n; sy++) {
-                    const double fx = dsub(ddiv((double)sx, (double)(n - 1)), 0.5);     // :1767-1768
-                    const double fy = dsub(ddiv((double)sy, (double)(n - 1)), 0.5);
-                    d3 start, dir; bool is_view;
-                    if (f.focal_blur) {
-                        const d3 sv = mk(dmul(ddiv(fx, (double)W), f.focal_strength), dmul(ddiv(fy, (double)H), f.focal_strength),
-                                         -in0.pos_z);                                     // :1776-1778
-                        start = mul3x3(in0.Minv, sv);
-                        dir = vsub(focal_pt, start);                                      // :1790
-                        is_view = false;
-                    } else {
-                        start = mk(in0.start[0], in0.start[1], in0.start[2]);
-                        dir = mk(-dsub(ddiv(dadd((double)col, fx), (double)W), 0.5),
-                                 dmul(-dsub(ddiv(dadd((double)row, fy), (double)H), 0.5), f.aspect), f.fov_depth);   // :1794-1796
-                        is_view = true;
-                    }
-                    n_primary++;
-                    const PixelOut s1 = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, &n_shadow,
-                                                         &n_secondary, &hit);
-                    if (hit) n_hits++;
-                    sum_r += (s1.color >> 16) & 0xff; sum_g += (s1.color >> 8) & 0xff; sum_b += s1.color & 0xff;
-                    po.id = s1.id;
-                }
-            }
-            const int nn = n * n;
-            sum_r /= nn; sum_g /= nn; sum_b /= nn;                                        // :1820-1822
-            po.color = 0xff000000u | ((uint32_t)(sum_r & 0xff) << 16) | ((uint32_t)(sum_g & 0xff) << 8) | (uint32_t)(sum_b & 0xff);
+            const d3 dw = mul3x3(in0.Minv, dir_view);
+            focal_pt = vadd(vscale(dw, f.focal_depth), mk(in0.start[0], in0.start[1], in0.start[2]));       // :1759
         }
+        const int nn = n * n;
+        for (int si = 0; si < nn; si++) {
+            const int sx = si / n, sy = si - sx * n;                                      // subX outer, subY inner (:1762-1764)
+            double fx = 0.0, fy = 0.0;
+            if (n > 1) {
+                fx = dsub(ddiv((double)sx, (double)(n - 1)), 0.5);                        // :1767-1768
+                fy = dsub(ddiv((double)sy, (double)(n - 1)), 0.5);
+            }
+            d3 start, dir; bool is_view;
+            if (focal) {
+                const d3 sv = mk(dmul(ddiv(fx, (double)W), f.focal_strength), dmul(ddiv(fy, (double)H), f.focal_strength),
+                                 -in0.pos_z);                                             // :1776-1778
+                start = mul3x3(in0.Minv, sv);
+                dir = vsub(focal_pt, start);                                              // :1790
+                is_view = false;
+            } else {
+                start = mk(in0.start[0], in0.start[1], in0.start[2]);
+                dir = mk(-dsub(ddiv(dadd((double)col, fx), (double)W), 0.5),
+                         dmul(-dsub(ddiv(dadd((double)row, fy), (double)H), 0.5), f.aspect), f.fov_depth);   // :1728, :1794-1796
+                is_view = true;
+            }
+            n_primary++;
+            const PixelOut s1 = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, &xc, &n_shadow, &n_secondary,
+                                                 &hit);
+            if (hit) n_hits++;
+            sum_r += (s1.color >> 16) & 0xff; sum_g += (s1.color >> 8) & 0xff; sum_b += s1.color & 0xff;
+            po.id = s1.id;
+        }
+        sum_r /= nn; sum_g /= nn; sum_b /= nn;                                            // :1820-1822
+        po.color = 0xff000000u | ((uint32_t)(sum_r & 0xff) << 16) | ((uint32_t)(sum_g & 0xff) << 8) | (uint32_t)(sum_b & 0xff);
         const size_t idx = (size_t)row * (size_t)W + (size_t)col;
         pixels[idx] = po.color;                                                            // Surface.DrawPixel
         if (hit_ids) hit_ids[idx] = po.id;
     }
 
     // one atomic per warp per counter
-    unsigned long long v[12] = {n_primary, n_shadow, n_secondary, c.node_visits, c.prim_tests, c.sphere_tests, n_hits, c.shaded,
-                                c.filter_tests, c.filter_unsure, c.filter_mismatch, c.bundled};
+    unsigned long long v[12] = {n_primary, n_shadow, n_secondary, (unsigned long long)c.node_visits + xc.node_visits,
+                                (unsigned long long)c.prim_tests + xc.prim_tests, (unsigned long long)c.sphere_tests + xc.sphere_tests,
+                                n_hits, c.shaded, (unsigned long long)c.filter_tests + xc.filter_tests,
+                                (unsigned long long)c.filter_unsure + xc.filter_unsure,
+                                (unsigned long long)c.filter_mismatch + xc.filter_mismatch, c.bundled};
 #pragma unroll
     for (int k = 0; k < 12; k++) {
         unsigned long long x = v[k];
