@@ -26,9 +26,9 @@ METRIC = "Mrays/s (primary+shadow+secondary)"
 UNIT = "Mrays/s"
 
 # Algorithmic work model of SURVEY.md section 8(d): flops per unit (FMA = 2, everything else 1)
-FLOPS = dict(primary=22, primary_aa=26, tri_test=41, sphere_test=34, node=40, phong=112, lambert=80, shadow_setup=6,
-             reflect_setup=14, texture=12)
-BYTES = dict(node=64, tri=128, sphere=48, pixel=4)   # what ONE visit / test / pixel has to move
+FLOPS = dict(primary=22, primary_aa=26, tri_test=41, tri_filter=11, sphere_test=34, node=40, phong=112, lambert=80,
+             shadow_setup=6, reflect_setup=14, texture=12)
+BYTES = dict(node=64, tri=128, tri_filter=64, sphere=48, pixel=4)   # what ONE visit / test / pixel has to move
 
 
 def workload(name, scale=1.0):
@@ -55,16 +55,20 @@ def workload(name, scale=1.0):
 
 
 def algorithmic_work(st, frame):
-    """(flops, bytes) of one step from the kernel's counters."""
+    """(flops32, flops64, bytes) of one step from the kernel's counters.
+    FP32: BVH node visits and the filtered triangle tests (charged their back-face-reject cost: most end
+    there).  FP64: the reference-arithmetic primitive tests, ray generation, shading, ray setup."""
     tri_tests = st["prim_tests"] - st["sphere_tests"]
     shade = (FLOPS["phong"] if frame.specular_lighting else FLOPS["lambert"]) if frame.shading else 0
-    flops = (st["rays_primary"] * (FLOPS["primary_aa"] if frame.sub_pixel_res > 1 else FLOPS["primary"])
-             + st["node_visits"] * FLOPS["node"] + tri_tests * FLOPS["tri_test"] + st["sphere_tests"] * FLOPS["sphere_test"]
-             + st["shaded_hits"] * (shade + (FLOPS["texture"] if frame.texture3d_id else 0))
-             + st["rays_shadow"] * FLOPS["shadow_setup"] + st["rays_secondary"] * FLOPS["reflect_setup"])
-    nbytes = (st["node_visits"] * BYTES["node"] + tri_tests * BYTES["tri"] + st["sphere_tests"] * BYTES["sphere"]
-              + frame.width * frame.height * BYTES["pixel"])
-    return float(flops), float(nbytes)
+    traced_shadow = st["rays_shadow"] - st.get("rays_bundled", 0)
+    flops32 = st["node_visits"] * FLOPS["node"] + st.get("filter_tests", 0) * FLOPS["tri_filter"]
+    flops64 = (st["rays_primary"] * (FLOPS["primary_aa"] if frame.sub_pixel_res > 1 else FLOPS["primary"])
+               + tri_tests * FLOPS["tri_test"] + st["sphere_tests"] * FLOPS["sphere_test"]
+               + st["shaded_hits"] * (shade + (FLOPS["texture"] if frame.texture3d_id else 0))
+               + traced_shadow * FLOPS["shadow_setup"] + st["rays_secondary"] * FLOPS["reflect_setup"])
+    nbytes = (st["node_visits"] * BYTES["node"] + tri_tests * BYTES["tri"] + st.get("filter_tests", 0) * BYTES["tri_filter"]
+              + st["sphere_tests"] * BYTES["sphere"] + frame.width * frame.height * BYTES["pixel"])
+    return float(flops32), float(flops64), float(nbytes)
 
 
 class ClockSampler(threading.Thread):
@@ -338,31 +342,44 @@ def main():
                "note": "softray_render (C ABI) with a pinned host framebuffer; the scene is resident "
                        "(uploaded once by softray_scene_create, like the reference caches its geometry)"}
 
-    # ---- roofline of the render kernel: FP64 issue (this path is branchy FP64, not HBM/tensor)
-    flops, nbytes = algorithmic_work(counters, frame)
+    # ---- roofline of the render kernel: FP issue (branchy FP32 search + FP64 reference arithmetic; not
+    # HBM-bound, not tensor work).  Mixed-precision rule of SURVEY 8d: FP32 work against the measured
+    # FFMA peak, FP64 work against the measured DFMA peak; frac = share of the minimum possible issue time.
+    flops32, flops64, nbytes = algorithmic_work(counters, frame)
     peak64 = ctx.measure_fma_peak(True)
     peak32 = ctx.measure_fma_peak(False)
-    achieved = flops / (kernel_ms * 1e-3) / 1e12
+    t_s = kernel_ms * 1e-3
+    achieved = (flops32 + flops64) / t_s / 1e12
+    t_min = (flops32 / (peak32 * 1e12) + flops64 / (peak64 * 1e12)) / world if peak32 > 0 and peak64 > 0 else 0.0
+    eff_peak = (flops32 + flops64) / t_min / 1e12 if t_min > 0 else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:   # dram bytes of one launch of this workload from the committed ncu capture, if there is one
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
     roofline = {
-        "bound": "fp64-issue", "achieved": achieved, "peak": peak64 * world, "unit": "TFLOP/s",
-        "frac": achieved / (peak64 * world) if peak64 > 0 else None, "traffic": None,
+        "bound": "fp-issue", "achieved": achieved, "peak": eff_peak, "unit": "TFLOP/s",
+        "frac": (t_min / t_s) if t_s > 0 else None, "traffic": traffic,
         "kernel": "sr::render_kernel", "kernel_ms": kernel_ms,
-        "peak_source": "measured in this run by softray_measure_fma_peak (DFMA chain, FMA = 2 flops); "
-                       "MEASURED_PEAKS.json has no vector-FP64 figure",
-        "fp32_fma_peak_tflops": peak32,
-        "note": "the reference arithmetic is unfused (separate DMUL/DADD, SURVEY App. A #18), so issue-slot "
-                "utilisation is about 2x this fraction",
-        "hbm": {"achieved": nbytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
-                "frac": nbytes / (kernel_ms * 1e-3) / 1e9 / (hbm_peak * world),
+        "flops_fp32": flops32, "flops_fp64": flops64,
+        "fp32_fma_peak_tflops": peak32 * world, "fp64_fma_peak_tflops": peak64 * world,
+        "peak_source": "measured in this run by softray_measure_fma_peak (FFMA / DFMA chains, FMA = 2 flops); "
+                       "MEASURED_PEAKS.json has no vector-FP figure.  peak = the flop-weighted mix of the two "
+                       "(flops / minimum issue time), frac = minimum issue time / kernel time",
+        "note": "algorithmic flops = SURVEY 8d constants x the kernel's own counters; a BVH walk is mostly "
+                "min/max/compare/load issue slots, which this model does not credit (ncu issue-slot "
+                "utilisation is in profiles/)",
+        "hbm": {"achieved": nbytes / t_s / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
+                "frac": nbytes / t_s / 1e9 / (hbm_peak * world),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback",
-                "note": "algorithmic bytes of all node/primitive fetches; the scene is L1/L2 resident, so this is "
-                        "cache traffic, not DRAM traffic"},
+                "note": "algorithmic bytes of all node / primitive fetches; they are served by L1/L2 (the "
+                        "scene is cache resident at this size), DRAM traffic is `traffic`"},
     }
 
     cpu_baseline = None
