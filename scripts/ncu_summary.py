@@ -1,0 +1,36 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep (one kernel launch, --set full) into the text file committed under profiles/.
+usage: ncu_summary.py <report.ncu-rep> <out.txt> "<header line>" """
+import csv
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__warps_eligible.avg.per_cycle_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg",
+    "sm__cycles_active.avg",
+]
+
+
+def main():
+    rep, out, header = sys.argv[1], sys.argv[2], sys.argv[3]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    lines = [header]
+    for i, h in enumerate(hdr):
+        stall = "average_warps_issue_stalled" in h and h.endswith("per_issue_active.ratio")
+        if h in WANT or (stall and float(vals[i] or 0) >= 0.1):
+            lines.append(f"{h} = {vals[i]} {units[i]}")
+    open(out, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main()
