@@ -49,6 +49,10 @@ struct softray_ctx {
     DevCounters* d_counters = nullptr;
     // pinned host staging for the frame constants and the counters
     DevInstance* h_insts = nullptr;
+    // per-frame TLAS over the instances of a composite frame (pinned staging + device copy)
+    BvhNode* h_tlas_nodes = nullptr; BvhNode* d_tlas_nodes = nullptr;
+    int32_t* h_tlas_order = nullptr; int32_t* d_tlas_order = nullptr;
+    int32_t tlas_nodes_used = 0;
     double* h_offsets = nullptr;
     DevCounters* h_counters = nullptr;
     // device framebuffer of the host-buffer entry point (grown on demand)
@@ -64,6 +68,8 @@ struct softray_scene {
     DevScene dev;                      // passed to the kernel by value
     std::vector<void*> allocs;         // every device allocation of this scene
     std::vector<int32_t> mesh_tris;    // n_tris per mesh (hit-id bases)
+    struct V3 { double v[3]; };
+    std::vector<V3> mesh_bmin, mesh_bmax;   // Model.Min/Max per mesh (per-frame instance hierarchy)
     uint64_t fingerprint = 1469598103934665603ull;
     size_t device_bytes = 0;
     double all_min[3] = {1e300, 1e300, 1e300}, all_max[3] = {-1e300, -1e300, -1e300};   // every primitive
@@ -361,6 +367,7 @@ extern "C" void softray_destroy(softray_ctx* ctx)
     cudaFree(ctx->d_insts); cudaFree(ctx->d_offsets); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_counters);
     cudaFree(ctx->d_pixels); cudaFree(ctx->d_ids);
     cudaFreeHost(ctx->h_insts); cudaFreeHost(ctx->h_offsets); cudaFreeHost(ctx->h_counters);
+    cudaFree(ctx->d_tlas_nodes); cudaFree(ctx->d_tlas_order); cudaFreeHost(ctx->h_tlas_nodes); cudaFreeHost(ctx->h_tlas_order);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -393,6 +400,10 @@ extern "C" int softray_create(int32_t device_ordinal, softray_ctx** out)
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_tile_counter, sizeof(unsigned int)));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_counters, sizeof(DevCounters)));
         SR_CUDA(ctx, cudaMallocHost((void**)&ctx->h_insts, sizeof(DevInstance) * SOFTRAY_MAX_INSTANCES));
+        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_tlas_nodes, sizeof(BvhNode) * SOFTRAY_MAX_INSTANCES));
+        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_tlas_order, sizeof(int32_t) * SOFTRAY_MAX_INSTANCES));
+        SR_CUDA(ctx, cudaMallocHost((void**)&ctx->h_tlas_nodes, sizeof(BvhNode) * SOFTRAY_MAX_INSTANCES));
+        SR_CUDA(ctx, cudaMallocHost((void**)&ctx->h_tlas_order, sizeof(int32_t) * SOFTRAY_MAX_INSTANCES));
         SR_CUDA(ctx, cudaMallocHost((void**)&ctx->h_offsets, sizeof(double) * 3 * SOFTRAY_MAX_SHADOW_SAMPLES));
         SR_CUDA(ctx, cudaMallocHost((void**)&ctx->h_counters, sizeof(DevCounters)));
         return SOFTRAY_OK;
@@ -458,6 +469,8 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
         }
         dm.scale = round_up(max_abs3(m.bbox_min, m.bbox_max));
         sc->mesh_tris.push_back(m.n_tris);
+        { softray_scene::V3 a, b; for (int k = 0; k < 3; k++) { a.v[k] = m.bbox_min[k]; b.v[k] = m.bbox_max[k]; }
+          sc->mesh_bmin.push_back(a); sc->mesh_bmax.push_back(b); }
         if (m.n_tris == 0) continue;
         if (brute) {
             int rc = upload(sc, recs, &dm.tris);
@@ -715,6 +728,39 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
         d.sph_can_shadow = (f.shadows && scene->dev.n_spheres > 0) ? spheres_can_shadow(scene, f, d, ctx->h_offsets) : 0;
     }
 
+    // composite frame: BVH over the view-space boxes of the instances (the reference traces
+    // instances one after the other over the whole frame, Renderer.cs:746-755)
+    f.tlas_nodes = nullptr; f.tlas_order = nullptr; ctx->tlas_nodes_used = 0;
+    if (fr->n_instances > 1 && scene->dev.accel == SOFTRAY_ACCEL_BVH) {
+        std::vector<PrimBounds> boxes((size_t)fr->n_instances);
+        double big = 0.0;
+        for (int32_t i = 0; i < fr->n_instances; i++) {
+            const softray_instance& in = fr->instances[i];
+            const double* mn = scene->mesh_bmin[(size_t)in.mesh_id].v; const double* mx = scene->mesh_bmax[(size_t)in.mesh_id].v;
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int corner = 0; corner < 8; corner++) {
+                const hv p = hmk((corner & 1) ? mx[0] : mn[0], (corner & 2) ? mx[1] : mn[1], (corner & 4) ? mx[2] : mn[2]);
+                const hv q = hmul3x4(in.M, p);
+                const double c[3] = {q.x, q.y, q.z};
+                for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], c[k]); hi[k] = std::fmax(hi[k], c[k]); }
+            }
+            for (int k = 0; k < 3; k++) {
+                // 1e-9: the box tolerance of the clip (1e-10) and the FP64 rounding of the transform
+                boxes[(size_t)i].lo[k] = round_down(lo[k] - 1e-9 - 1e-12 * std::fabs(lo[k]));
+                boxes[(size_t)i].hi[k] = round_up(hi[k] + 1e-9 + 1e-12 * std::fabs(hi[k]));
+                big = std::fmax(big, std::fmax(std::fabs(lo[k]), std::fabs(hi[k])));
+            }
+        }
+        BvhBuild tlas;
+        build_bvh(boxes, traversal_pad(big), 2, 4.0, &tlas);
+        if ((int)tlas.nodes.size() > SOFTRAY_MAX_INSTANCES || tlas.depth >= kStackEntries)
+            return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_render: instance hierarchy too large");
+        std::memcpy(ctx->h_tlas_nodes, tlas.nodes.data(), tlas.nodes.size() * sizeof(BvhNode));
+        std::memcpy(ctx->h_tlas_order, tlas.order.data(), tlas.order.size() * sizeof(int32_t));
+        ctx->tlas_nodes_used = (int32_t)tlas.nodes.size();
+        f.tlas_nodes = ctx->d_tlas_nodes; f.tlas_order = ctx->d_tlas_order;
+    }
+
     // one warp per 8x4-pixel tile, pulled from an atomic queue by persistent warps
     const int n_bands = (rows + f.band_height - 1) / f.band_height;
     const int my_bands = f.band_index < n_bands ? (n_bands - f.band_index + f.band_count - 1) / f.band_count : 0;
@@ -743,6 +789,12 @@ int enqueue_frame(softray_ctx* ctx, const softray_scene* scene, const Prepared& 
     if (f.shadows)
         SR_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, ctx->h_offsets, sizeof(double) * 3 * (size_t)f.shadow_samples,
                                      cudaMemcpyHostToDevice, stream));
+    if (ctx->tlas_nodes_used > 0) {
+        SR_CUDA(ctx, cudaMemcpyAsync(ctx->d_tlas_nodes, ctx->h_tlas_nodes, sizeof(BvhNode) * (size_t)ctx->tlas_nodes_used,
+                                     cudaMemcpyHostToDevice, stream));
+        SR_CUDA(ctx, cudaMemcpyAsync(ctx->d_tlas_order, ctx->h_tlas_order, sizeof(int32_t) * (size_t)f.n_instances,
+                                     cudaMemcpyHostToDevice, stream));
+    }
     SR_CUDA(ctx, cudaEventRecord(ctx->ev_staged, stream));
     ctx->staging_busy = true;
     SR_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned int), stream));

@@ -1075,15 +1075,66 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
         dir0 = dirs_are_view ? mul3x3(in.Minv, dirs_view_or_world[0]) : dirs_view_or_world[0];
         hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, xc);
     } else {
-        // extension: nearest hit across instances, ties to the lowest instance
+        // extension: nearest hit across instances, ties to the lowest instance.  Rigid
+        // transforms keep |dir|, so every instance's rayFrac is the parameter along dirs_view_or_world[0]
+        // from the view origin and the instance hierarchy can cull with it.
         double best = kNoHit;
-        for (int i = 0; i < f.n_instances; i++) {
-            const DevInstance& in = insts[i];
-            const d3 d = mul3x3(in.Minv, dirs_view_or_world[0]);
-            Hit hi;
-            if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]), d, &hi, xc) &&
-                hi.rf < best) {
-                best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
+        const d3 dv = dirs_view_or_world[0];
+        if (f.tlas_nodes != nullptr) {
+            FRay tr;
+            tr.ox = tr.oy = tr.oz = 0.0f;
+            tr.gx = __double2float_rn(dv.x); tr.gy = __double2float_rn(dv.y); tr.gz = __double2float_rn(dv.z);
+            tr.ix = __fdiv_rn(1.0f, tr.gx); tr.iy = __fdiv_rn(1.0f, tr.gy); tr.iz = __fdiv_rn(1.0f, tr.gz);
+            tr.nox = tr.noy = tr.noz = 0.0f;         // the view origin itself: the slab test is (plane * 1/g)
+            tr.tcull = CUDART_INF_F;
+            int stack[kStackEntries];
+            int sp = 0, cur = 0;
+            for (;;) {
+                if (cur >= 0) {
+                    const float4* p = reinterpret_cast<const float4*>(f.tlas_nodes + cur);
+                    const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+                    const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
+                    c->node_visits++;
+                    float t0, t1;
+                    const bool h0 = fslab(tr, a.x, a.y, a.z, a.w, b.x, b.y, &t0);
+                    const bool h1 = fslab(tr, b.z, b.w, cc.x, cc.y, cc.z, cc.w, &t1);
+                    if (h0 && h1) {
+                        const bool first0 = t0 <= t1;
+                        stack[sp++] = first0 ? d.y : d.x;
+                        cur = first0 ? d.x : d.y;
+                        continue;
+                    }
+                    if (h0) { cur = d.x; continue; }
+                    if (h1) { cur = d.y; continue; }
+                } else {
+                    const int code = -1 - cur;
+                    const int first = code >> 4, count = code & 15;
+                    for (int j = 0; j < count; j++) {
+                        const int i = __ldg(f.tlas_order + first + j);
+                        const DevInstance& in = insts[i];
+                        const d3 d = mul3x3(in.Minv, dv);
+                        Hit hi;
+                        if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]),
+                                        d, &hi, xc) &&
+                            (hi.rf < best || (hi.rf == best && i < which))) {
+                            best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
+                            tr.tcull = __double2float_ru(best) * 1.00002f + 1e-6f;
+                        }
+                    }
+                }
+                if (sp == 0) break;
+                cur = stack[--sp];
+            }
+        } else {
+            for (int i = 0; i < f.n_instances; i++) {
+                const DevInstance& in = insts[i];
+                const d3 d = mul3x3(in.Minv, dv);
+                Hit hi;
+                if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]), d, &hi,
+                                xc) &&
+                    hi.rf < best) {
+                    best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
+                }
             }
         }
     }

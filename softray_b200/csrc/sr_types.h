@@ -123,6 +123,9 @@ struct DevFrame {
     float   light_radius;       // >= the length of every area-light offset (0.2, ShadowMethod.cs:10), rounded up
     int32_t bundle_budget;      // node visits a shadow-bundle cone walk may spend before giving up (0 = no bundles)
     int32_t _pad;
+    // composite frames (n_instances > 1): a BVH over the view-space boxes of the instances, rebuilt per frame
+    const BvhNode* tlas_nodes;  // leaf primitives index tlas_order
+    const int32_t* tlas_order;  // instance index of the k-th TLAS leaf primitive
 };
 
 struct DevCounters {            // summed over the launch with one atomic per warp per counter
