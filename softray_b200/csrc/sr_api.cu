@@ -325,7 +325,7 @@ inline double sah_isect_cost(double dflt)
     return dflt;
 }
 
-constexpr int kBundleMinSamples = 16, kBundleBudget = 192;
+constexpr int kBundleMinSamples = 16, kBundleBudget = 384;   // budget counts child boxes: 384 = 192 nodes
 inline int env_int(const char* name, int dflt)
 {
     const char* e = std::getenv(name);
@@ -753,7 +753,7 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
         }
         BvhBuild tlas;
         build_bvh(boxes, traversal_pad(big), 2, 4.0, &tlas);
-        if ((int)tlas.nodes.size() > SOFTRAY_MAX_INSTANCES || tlas.depth >= kStackEntries)
+        if ((int)tlas.nodes.size() > SOFTRAY_MAX_INSTANCES || tlas.depth >= kTlasStackEntries)
             return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_render: instance hierarchy too large");
         std::memcpy(ctx->h_tlas_nodes, tlas.nodes.data(), tlas.nodes.size() * sizeof(BvhNode));
         std::memcpy(ctx->h_tlas_order, tlas.order.data(), tlas.order.size() * sizeof(int32_t));
