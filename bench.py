@@ -74,7 +74,7 @@ def algorithmic_work(st, frame):
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU during the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
