@@ -1168,6 +1168,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     }
     __syncthreads();
 
+    __shared__ int s_acc[4][32][4];           // per warp, per pixel of its tile: sums of R, G, B and the hit id
     const int lane = threadIdx.x & 31;
     const int W = f.width, H = f.height, n = f.sub_pixel_res;
     const int n_tiles = f.tiles_x * f.tiles_y;
@@ -1200,36 +1201,38 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
         if (tile >= n_tiles) break;
 #endif
         const int ty = tile / f.tiles_x, tx = tile - ty * f.tiles_x;
-        const int col = tx * 8 + (lane & 7);
         const int band_j = ty / f.tiles_per_band;
-        const int band_r = (ty - band_j * f.tiles_per_band) * 4 + (lane >> 3);
-        const int row = f.start_row + (f.band_index + band_j * f.band_count) * f.band_height + band_r;
-        if (col >= W || band_r >= f.band_height || row > f.end_row) continue;
+        const int row0 = f.start_row + (f.band_index + band_j * f.band_count) * f.band_height;
+        const int band_r0 = (ty - band_j * f.tiles_per_band) * 4;
 
-        // one loop for 1 spp (Renderer.cs:1722-1743) and n x n sub-pixels (:1744-1826): with n == 1 the
-        // sub-pixel fraction is 0.0 and (col + 0.0) / W is bit-identical to col / W
-        PixelOut po; bool hit = false;
-        po.color = 0; po.id = -1;
-        int sum_r = 0, sum_g = 0, sum_b = 0;
-        const DevInstance& in0 = s_insts[0];
-        const bool focal = f.focal_blur && n > 1;                                         // App. A #11
-        d3 focal_pt = mk(0, 0, 0);
-        if (focal) {
-            const d3 dir_view = mk(-dsub(ddiv((double)col, (double)W), 0.5),
-                                   dmul(-dsub(ddiv((double)row, (double)H), 0.5), f.aspect), f.fov_depth);
-            const d3 dw = mul3x3(in0.Minv, dir_view);
-            focal_pt = vadd(vscale(dw, f.focal_depth), mk(in0.start[0], in0.start[1], in0.start[2]));       // :1759
-        }
+        // The work items of a tile are its (pixel, sub-pixel) pairs, pixel-major, 32 at a time across the
+        // lanes: with n x n supersampling the lanes of a warp hold sub-rays of the SAME pixel (or of a few
+        // adjacent ones), which traverse almost identically, instead of 32 different pixels' rays looping
+        // over their sub-rays out of step.  Sums are integer (Renderer.cs:1811-1822), so the order in which
+        // the sub-rays arrive is irrelevant.  1 spp: one item per pixel, lane == pixel.
+        int* acc = s_acc[threadIdx.x >> 5][lane];
+        acc[0] = 0; acc[1] = 0; acc[2] = 0; acc[3] = -1;
+        __syncwarp();
         const int nn = n * n;
-        for (int si = 0; si < nn; si++) {
+        for (int w = lane; w < 32 * nn; w += 32) {
+            const int px = w / nn, si = w - px * nn;
+            const int col = tx * 8 + (px & 7);
+            const int band_r = band_r0 + (px >> 3);
+            const int row = row0 + band_r;
+            if (col >= W || band_r >= f.band_height || row > f.end_row) continue;
             const int sx = si / n, sy = si - sx * n;                                      // subX outer, subY inner (:1762-1764)
-            double fx = 0.0, fy = 0.0;
+            double fx = 0.0, fy = 0.0;                                                    // n == 1: (col + 0.0) / W == col / W
             if (n > 1) {
                 fx = dsub(ddiv((double)sx, (double)(n - 1)), 0.5);                        // :1767-1768
                 fy = dsub(ddiv((double)sy, (double)(n - 1)), 0.5);
             }
+            const DevInstance& in0 = s_insts[0];
             d3 start, dir; bool is_view;
-            if (focal) {
+            if (f.focal_blur && n > 1) {                                                  // App. A #11
+                const d3 dir_view = mk(-dsub(ddiv((double)col, (double)W), 0.5),
+                                       dmul(-dsub(ddiv((double)row, (double)H), 0.5), f.aspect), f.fov_depth);
+                const d3 dw = mul3x3(in0.Minv, dir_view);
+                const d3 focal_pt = vadd(vscale(dw, f.focal_depth), mk(in0.start[0], in0.start[1], in0.start[2]));   // :1759
                 const d3 sv = mk(dmul(ddiv(fx, (double)W), f.focal_strength), dmul(ddiv(fy, (double)H), f.focal_strength),
                                  -in0.pos_z);                                             // :1776-1778
                 start = mul3x3(in0.Minv, sv);
@@ -1242,17 +1245,34 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
                 is_view = true;
             }
             n_primary++;
+            bool hit = false;
             const PixelOut s1 = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, &xc, &n_shadow, &n_secondary,
                                                  &hit);
             if (hit) n_hits++;
-            sum_r += (s1.color >> 16) & 0xff; sum_g += (s1.color >> 8) & 0xff; sum_b += s1.color & 0xff;
-            po.id = s1.id;
+            int* pa = s_acc[threadIdx.x >> 5][px];
+            if (nn == 1) {
+                pa[0] = (int)((s1.color >> 16) & 0xff); pa[1] = (int)((s1.color >> 8) & 0xff); pa[2] = (int)(s1.color & 0xff);
+            } else {
+                atomicAdd(pa + 0, (int)((s1.color >> 16) & 0xff));
+                atomicAdd(pa + 1, (int)((s1.color >> 8) & 0xff));
+                atomicAdd(pa + 2, (int)(s1.color & 0xff));
+            }
+            if (si == nn - 1) pa[3] = s1.id;                                              // hit id of the last sub-ray
         }
-        sum_r /= nn; sum_g /= nn; sum_b /= nn;                                            // :1820-1822
-        po.color = 0xff000000u | ((uint32_t)(sum_r & 0xff) << 16) | ((uint32_t)(sum_g & 0xff) << 8) | (uint32_t)(sum_b & 0xff);
-        const size_t idx = (size_t)row * (size_t)W + (size_t)col;
-        pixels[idx] = po.color;                                                            // Surface.DrawPixel
-        if (hit_ids) hit_ids[idx] = po.id;
+        __syncwarp();
+        {
+            const int col = tx * 8 + (lane & 7);
+            const int band_r = band_r0 + (lane >> 3);
+            const int row = row0 + band_r;
+            if (col < W && band_r < f.band_height && row <= f.end_row) {
+                const int sum_r = acc[0] / nn, sum_g = acc[1] / nn, sum_b = acc[2] / nn;  // :1820-1822
+                const size_t idx = (size_t)row * (size_t)W + (size_t)col;
+                pixels[idx] = 0xff000000u | ((uint32_t)(sum_r & 0xff) << 16) | ((uint32_t)(sum_g & 0xff) << 8) |
+                              (uint32_t)(sum_b & 0xff);                                   // Surface.DrawPixel
+                if (hit_ids) hit_ids[idx] = acc[3];
+            }
+        }
+        __syncwarp();
     }
 
     // one atomic per warp per counter
