@@ -578,11 +578,15 @@ __device__ __forceinline__ int tri_filter(const TriFilt* __restrict__ t, const F
     return 2;                                                            // also every NaN / inf case
 }
 
-// BVH walk with the filter at the leaves.  0 surely clear, 1 surely occluded, 2 cannot tell.
+// BVH walk with the filter at the leaves.  0 surely clear, 1 surely occluded, 2 cannot tell: then
+// unsure[0..*n_unsure) lists the triangles the exact arithmetic has to look at (every other triangle is
+// surely missed); *n_unsure > kMaxCand means too many to list.
 __device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, const FRay& r,
-                                               float V, Counters* c)
+                                               float V, int* unsure, int* n_unsure, Counters* c)
 {
-    int result = 0;
+    bool hit = false;
+    int nu = 0;
+    int u0 = -1, u1 = -1, u2 = -1, u3 = -1;
     unsigned int nf = 0;
     c->node_visits += walk_bvh(
         nodes, c->stack,
@@ -594,24 +598,40 @@ __device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes
                 nf++;
                 float tau, etau;
                 const int res = tri_filter<false>(filt + first + i, r, V, r.tmax_hi, &tau, &etau);
-                if (res) { result = res; return true; }
+                if (res == 1) { hit = true; return true; }
+                if (res == 2) {
+                    if (nu == 0) u0 = first + i; else if (nu == 1) u1 = first + i; else if (nu == 2) u2 = first + i;
+                    else if (nu == 3) u3 = first + i;
+                    nu++;
+                }
             }
             return false;
         });
     c->filter_tests += nf;
-    return result;
+    if (hit) return 1;
+    if (nu == 0) return 0;
+    unsure[0] = u0; unsure[1] = u1; unsure[2] = u2; unsure[3] = u3;
+    *n_unsure = nu;
+    return 2;
 }
 
 // Nearest hit with the filter at the leaves.  Tracks the sure hit with the smallest upper bound
 // (best) and the smallest lower bound of every OTHER candidate, sure or not (other_lo): the winner of
 // the exact arithmetic is known iff best_hi < other_lo.
-struct FClosest { float best_lo, best_hi, other_lo; int best_k; };
+constexpr int kMaxCand = 4;
+// best_k < 0: no sure hit.  cand[0..n_cand): every triangle that is not surely missed (incl. the best);
+// n_cand > kMaxCand: too many to list.  The exact winner is among the candidates whose lower bound does
+// not exceed best_hi (everything else is surely missed or surely behind the best sure hit).
+struct FClosest { float best_hi; int best_k; int n_cand; int cand[kMaxCand]; float cand_lo[kMaxCand]; };
 
 __device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, FRay& r,
                                                     float V, FClosest* out, XCounters* c)
 {
-    float best_lo = 1e30f, best_hi = 1e30f, other_lo = 1e30f;
+    float best_hi = 1e30f;
     int best_k = -1;
+    int n_cand = 0;
+    int c0 = -1, c1 = -1, c2 = -1, c3 = -1;
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
     unsigned int nf = 0;
     c->node_visits += walk_bvh(
         nodes, c->stack,
@@ -625,18 +645,22 @@ __device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ 
                 const int res = tri_filter<true>(filt + first + i, r, V, best_hi, &tau, &etau);
                 if (res == 0) continue;
                 const float lo = tau - etau, hi = tau + etau;
+                if (n_cand == 0) { c0 = first + i; l0 = lo; }
+                else if (n_cand == 1) { c1 = first + i; l1 = lo; }
+                else if (n_cand == 2) { c2 = first + i; l2 = lo; }
+                else if (n_cand == 3) { c3 = first + i; l3 = lo; }
+                n_cand++;
                 if (res == 1 && hi < best_hi) {
-                    other_lo = fminf(other_lo, best_lo);
-                    best_lo = lo; best_hi = hi; best_k = first + i;
+                    best_hi = hi; best_k = first + i;
                     r.tcull = hi * 1.00002f + 1e-6f;
-                } else {
-                    other_lo = fminf(other_lo, lo);
                 }
             }
             return false;
         });
     c->filter_tests += nf;
-    out->best_lo = best_lo; out->best_hi = best_hi; out->other_lo = other_lo; out->best_k = best_k;
+    out->best_hi = best_hi; out->best_k = best_k; out->n_cand = n_cand;
+    out->cand[0] = c0; out->cand[1] = c1; out->cand[2] = c2; out->cand[3] = c3;
+    out->cand_lo[0] = l0; out->cand_lo[1] = l1; out->cand_lo[2] = l2; out->cand_lo[3] = l3;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -780,19 +804,22 @@ __device__ __noinline__ void spheres_closest_exact(const DevScene& sc, d3 s, d3 
     }
 }
 
-// only_k >= 0: test that one triangle only (the filter has proven it to be the winner)
-__device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivision, d3 s, d3 dir, int only_k, BestPrim* bt,
-                                                d3* ts_out, double* offset_out, XCounters* c)
+// n_list > 0: only the listed triangles (the filter has proven every other one missed or beaten)
+__device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivision, d3 s, d3 dir, const int* list, int n_list,
+                                                BestPrim* bt, d3* ts_out, double* offset_out, XCounters* c)
 {
     d3 ts = s; double offset = 0.0;
     *ts_out = s; *offset_out = 0.0;
     if (subdivision && !reference_clip(m.bmin, m.bmax, &ts, dir, &offset)) return;
     *ts_out = ts; *offset_out = offset;
-    if (only_k >= 0) {
-        double rf;
-        c->prim_tests++;
-        if (tri_intersect(m.tris + only_k, ts, dir, kNoHit, &rf)) {
-            bt->rf = rf; bt->k = only_k; bt->index = __ldg(reinterpret_cast<const int*>(m.tris + only_k) + 31);
+    if (n_list > 0) {
+        for (int j = 0; j < n_list; j++) {
+            const int k = list[j];
+            double rf;
+            c->prim_tests++;
+            if (!tri_intersect(m.tris + k, ts, dir, bt->rf, &rf)) continue;
+            const int index = __ldg(reinterpret_cast<const int*>(m.tris + k) + 31);
+            if (rf < bt->rf || (rf == bt->rf && index < bt->index)) { bt->rf = rf; bt->k = k; bt->index = index; }
         }
         return;
     }
@@ -823,31 +850,40 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
     BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
     d3 ts = s; double offset = 0.0;
     if (m.n_tris > 0) {
-        int known = 2;                                   // 0: surely no hit, 1: winner = fk, 2: ask the exact path
-        int fk = -1;
+        // 0: surely no hit; 1: the winner is among list[0..n_list) (one entry: it IS the winner); 2: full exact walk
+        int known = 2;
+        int list[kMaxCand]; int n_list = 0;
+        bool sure_hit = false;
         if (filter_mode != 1 && m.nodes != nullptr) {
             FRay r; double t0;
             known = fray_setup_fwd(m, subdivision, s, dir, &r, &t0);
             if (known == 1) {
                 FClosest fc;
                 walk_filter_closest(m.nodes, m.filt, r, m.scale, &fc, c);
-                if (fc.best_k >= 0 && fc.best_hi < fc.other_lo) fk = fc.best_k;
-                else known = (fc.best_k < 0 && fc.other_lo >= 1e30f) ? 0 : 2;
+                sure_hit = fc.best_k >= 0;
+                if (fc.n_cand == 0) known = 0;
+                else if (fc.n_cand > kMaxCand) known = 2;
+                else {
+                    for (int j = 0; j < fc.n_cand; j++)
+                        if (fc.cand[j] == fc.best_k || fc.cand_lo[j] <= fc.best_hi) list[n_list++] = fc.cand[j];
+                }
             }
         }
         if (filter_mode == 2) {
-            mesh_closest_exact(m, subdivision, s, dir, -1, &bt, &ts, &offset, c);
-            if ((known == 0 && bt.k >= 0) || (known == 1 && bt.k != fk)) c->filter_mismatch++;
-            if (known == 2) c->filter_unsure++;
-        } else {
-            if (known == 1) {
-                mesh_closest_exact(m, subdivision, s, dir, fk, &bt, &ts, &offset, c);
-                if (bt.k < 0) known = 2;                 // cannot happen if the bounds hold; stay correct anyway
-            }
-            if (known == 2) {
-                if (filter_mode != 1 && m.nodes != nullptr) c->filter_unsure++;
-                mesh_closest_exact(m, subdivision, s, dir, -1, &bt, &ts, &offset, c);
-            }
+            mesh_closest_exact(m, subdivision, s, dir, nullptr, 0, &bt, &ts, &offset, c);
+            bool in_list = bt.k < 0;
+            for (int j = 0; j < n_list; j++) in_list = in_list || list[j] == bt.k;
+            // contradictions: "surely nothing" but the exact walk hits; the exact winner is not a candidate;
+            // a sure hit exists but the exact walk finds nothing
+            if ((known == 0 && bt.k >= 0) || (known == 1 && !in_list) || (known == 1 && sure_hit && bt.k < 0))
+                c->filter_mismatch++;
+            if (known == 2 || n_list > 1) c->filter_unsure++;
+        } else if (known == 1) {
+            if (n_list > 1) c->filter_unsure++;
+            mesh_closest_exact(m, subdivision, s, dir, list, n_list, &bt, &ts, &offset, c);
+        } else if (known == 2) {
+            if (filter_mode != 1 && m.nodes != nullptr) c->filter_unsure++;
+            mesh_closest_exact(m, subdivision, s, dir, nullptr, 0, &bt, &ts, &offset, c);
         }
     }
     const double rf_tri = bt.k >= 0 ? dadd(bt.rf, offset) : kNoHit;   // SpatialSubdivision.cs:416
@@ -877,7 +913,8 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
 // "shadowInfo != null && shadowInfo.rayFrac <= 1.0" (ShadowMethod.cs:171): true iff ANY primitive
 // reports a rayFrac <= 1.0, because the minimum of the reported rayFracs is what the chain returns.
 // Exact (reference arithmetic) versions, one per primitive kind.
-__device__ __noinline__ bool occluded_mesh(const DevMesh& m, int subdivision, d3 s, d3 dir, XCounters* c)
+__device__ __noinline__ bool occluded_mesh(const DevMesh& m, int subdivision, d3 s, d3 dir, const int* list, int n_list,
+                                          XCounters* c)
 {
     BestPrim dummy; dummy.rf = kNoHit; dummy.k = -1; dummy.index = 0;
     if (m.n_tris <= 0) return false;
@@ -885,6 +922,14 @@ __device__ __noinline__ bool occluded_mesh(const DevMesh& m, int subdivision, d3
     if (subdivision && !reference_clip(m.bmin, m.bmax, &ts, dir, &offset)) return false;
     // rf + offset <= 1.0 needs rf <= 1.0 - offset (+ an ulp of slack for the walk's cull)
     const double limit = (1.0 - offset) * (1.0 + 1e-12) + 1e-300;
+    if (n_list > 0) {       // only the triangles the filter could not decide; every other one is surely missed
+        for (int j = 0; j < n_list; j++) {
+            double rf;
+            c->prim_tests++;
+            if (tri_intersect(m.tris + list[j], ts, dir, limit, &rf) && dadd(rf, offset) <= 1.0) return true;
+        }
+        return false;
+    }
     if (m.nodes) {
         double te = 0.0;
         // the clipped start already lies on/in the root box; otherwise enter it first
@@ -962,9 +1007,9 @@ __device__ __forceinline__ void shadow_ray(const DevFrame& f, const DevInstance&
 }
 
 __device__ __forceinline__ bool occluded_exact(const DevScene& sc, const DevInstance& in, const DevMesh& m, int subdivision,
-                                               d3 start, d3 dir, XCounters* c)
+                                               d3 start, d3 dir, const int* list, int n_list, XCounters* c)
 {
-    if (occluded_mesh(m, subdivision, start, dir, c)) return true;
+    if (occluded_mesh(m, subdivision, start, dir, list, n_list, c)) return true;
     return in.sph_can_shadow && occluded_spheres(sc, start, dir, c);
 }
 
@@ -996,42 +1041,37 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
         }
         if (all_clear && f.filter_mode != 2) escaped = n;
         else
-        // 32 samples at a time: the filter answers most rays; the undecided ones are collected in a
-        // bit mask and answered by the exact path afterwards, when the lanes of the warp that have
-        // any can run it together
-        for (int base = 0; base < n; base += 32) {
-            const int cnt = min(32, n - base);
-            unsigned int pending = 0;
+        for (int i = 0; i < n; i++) {
+            d3 start, dir;
+            shadow_ray(f, in, offsets, end, i, &start, &dir);
+            bool occ;
             if (use_filter) {
-                for (int j = 0; j < cnt; j++) {
-                    d3 start, dir;
-                    shadow_ray(f, in, offsets, end, base + j, &start, &dir);
-                    // anchor = the ray's far end (start + dir): `end` itself for a point light
-                    const d3 anchor = f.point_lighting ? end : vadd(start, dir);
-                    FRay r;
-                    int res = fray_setup(m, f.subdivision, anchor, dir, &r);
-                    if (res == 1) res = walk_filter_any(m.nodes, m.filt, r, m.scale, c);
-                    if (f.filter_mode == 2) {
-                        const bool occ = occluded_mesh(m, f.subdivision, start, dir, xc);
-                        if ((res == 0 && occ) || (res == 1 && !occ) || (all_clear && occ)) c->filter_mismatch++;
-                        if (res == 2) c->filter_unsure++;
-                        res = occ ? 1 : 0;
+                // anchor = the ray's far end (start + dir): `end` itself for a point light
+                const d3 anchor = f.point_lighting ? end : vadd(start, dir);
+                FRay r;
+                int list[kMaxCand]; int n_list = 0;
+                int res = fray_setup(m, f.subdivision, anchor, dir, &r);
+                if (res == 1) res = walk_filter_any(m.nodes, m.filt, r, m.scale, list, &n_list, c);
+                if (n_list > kMaxCand) n_list = 0;                  // too many undecided triangles: full exact walk
+                if (f.filter_mode == 2) {
+                    occ = occluded_mesh(m, f.subdivision, start, dir, nullptr, 0, xc);
+                    if ((res == 0 && occ) || (res == 1 && !occ) || (all_clear && occ)) c->filter_mismatch++;
+                    if (res == 2) {
+                        c->filter_unsure++;
+                        if (n_list > 0 && occluded_mesh(m, f.subdivision, start, dir, list, n_list, xc) != occ) c->filter_mismatch++;
                     }
-                    if (res == 0 && in.sph_can_shadow) res = occluded_spheres(sc, start, dir, xc) ? 1 : 0;
-                    if (res == 0) escaped++;
-                    else if (res == 2) pending |= 1u << j;
+                } else if (res == 2) {
+                    // the exact arithmetic looks only at the triangles the filter could not decide
+                    c->filter_unsure++;
+                    occ = occluded_mesh(m, f.subdivision, start, dir, list, n_list, xc);
+                } else {
+                    occ = res == 1;
                 }
+                if (!occ && in.sph_can_shadow) occ = occluded_spheres(sc, start, dir, xc);
             } else {
-                pending = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+                occ = occluded_exact(sc, in, m, f.subdivision, start, dir, nullptr, 0, xc);
             }
-            while (pending) {
-                const int j = __ffs((int)pending) - 1;
-                pending &= pending - 1;
-                d3 start, dir;
-                shadow_ray(f, in, offsets, end, base + j, &start, &dir);
-                if (use_filter) c->filter_unsure++;
-                if (!occluded_exact(sc, in, m, f.subdivision, start, dir, xc)) escaped++;
-            }
+            if (!occ) escaped++;
         }
         const double frac = ddiv((double)escaped, (double)n);
         color = modulate(color, to_byte(dmul(frac, 255.0)));
