@@ -234,6 +234,35 @@ int  softray_ipc_close(softray_ctx* ctx, void* d_ptr);
  * fp64 != 0 measures DFMA, else FFMA. */
 int  softray_measure_fma_peak(softray_ctx* ctx, int32_t fp64, double* tflops_out);
 
+/* ---- resolve (the step after the path) ---------------------------------------
+ * Renderer.PostProcessImage (Renderer.cs:819-898) then Renderer.AntiAliasImage (:937-978) in one device
+ * pass.  `src` is the surface the frame was traced into: (dst_w * aa_res) x (dst_h * aa_res) pixels
+ * (AntiAliasResolution multiplies the surface size, Renderer.cs:366-410,593-626); every source pixel goes
+ * through the style's colour function, then aa_res x aa_res blocks are summed per channel, divided
+ * (truncating) and packed with alpha 0xFF.  aa_res == 1: the styled surface, alpha untouched (dst may
+ * alias src).  The depth styles (DepthSmooth / DepthBanded / Normals) read the rasteriser's depth
+ * buffers and are not part of the raytrace path: SOFTRAY_E_UNSUPPORTED. */
+#define SOFTRAY_STYLE_STANDARD       0   /* Renderer.Style.Standard: nothing to do                  */
+#define SOFTRAY_STYLE_COLOR_SHUFFLE  1   /* ZRGB -> 0GBR                                            */
+#define SOFTRAY_STYLE_NEGATIVE       2   /* x == BackgroundColor ? x : 0x00ffffff - x (uint)        */
+int  softray_resolve(softray_ctx* ctx, const uint32_t* src_argb, int32_t dst_width, int32_t dst_height,
+                     int32_t aa_res, int32_t style, uint32_t background_argb, uint32_t* dst_argb);   /* host buffers */
+int  softray_resolve_device(softray_ctx* ctx, const uint32_t* d_src_argb, int32_t dst_width, int32_t dst_height,
+                            int32_t aa_res, int32_t style, uint32_t background_argb, uint32_t* d_dst_argb,
+                            void* stream);
+
+/* ---- model files (the on-disk format feeding the path) --------------------
+ * Model.Load3ds (Model.cs:522-653) + the 3dsLoader chunk parser (3dsLoader/ThreeDSFile.cs:132-662) +
+ * Model.PostProcessGeometry (Model.cs:750-790) + the per-triangle colour packing of
+ * MakeRayTracableGeometry_simple (Renderer.cs:1452-1469): a .3DS byte stream becomes the flattened,
+ * unit-cube-normalised arrays softray_scene_create takes.  Host code only (no device needed).
+ * Malformed input answers SOFTRAY_E_FORMAT (the FormatException of Model.cs:555). */
+typedef struct softray_model softray_model;
+int  softray_model_load_3ds(const uint8_t* bytes, uint64_t n_bytes, softray_model** out);
+/* fills `out` with pointers into the model, valid until softray_model_destroy */
+int  softray_model_get_mesh(const softray_model* model, softray_mesh* out);
+void softray_model_destroy(softray_model* model);
+
 /* ---- helpers that mirror small reference functions the shim would otherwise re-implement ---- */
 
 /* Instance.InitRender matrices (Instance.cs:134-135, Matrix.cs:74-168), computed with the C

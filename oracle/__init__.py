@@ -308,3 +308,26 @@ class Scene:
         if getattr(self, "_h", None) and _lib is not None:
             _lib.orc_scene_free(self._h)
             self._h = None
+
+
+def resolve(src, aa_res=1, style=0, background=0):
+    """Renderer.PostProcessImage (Renderer.cs:819-898; Standard / ColorShuffle / Negative) followed by
+    Renderer.AntiAliasImage (Renderer.cs:937-978), restated with numpy integer arithmetic.
+    src: (H*aa, W*aa) uint32.  TEST INFRASTRUCTURE ONLY."""
+    x = np.ascontiguousarray(src, dtype=np.uint32).copy()
+    if style == 1:      # ColorShuffle: ((x & 0xffff) << 8) + ((x >> 16) & 0xff)   (:829)
+        x = ((x & np.uint32(0xFFFF)) << np.uint32(8)) + ((x >> np.uint32(16)) & np.uint32(0xFF))
+    elif style == 2:    # Negative: x == BackgroundColor ? BackgroundColor : 0x00ffffff - x, unchecked uint   (:833)
+        with np.errstate(over="ignore"):
+            x = np.where(x == np.uint32(background), np.uint32(background), np.uint32(0x00FFFFFF) - x).astype(np.uint32)
+    elif style != 0:
+        raise OracleError(abi.E_UNSUPPORTED, "resolve style")
+    if aa_res < 2:
+        return x
+    h, w = x.shape[0] // aa_res, x.shape[1] // aa_res
+    blocks = x.reshape(h, aa_res, w, aa_res)
+    out = np.full((h, w), 255 << 24, dtype=np.uint64)
+    for sh in (16, 8, 0):   # Surface.UnpackRgb, int sums, truncating divide, Surface.PackRgb (:946-975)
+        s_ = ((blocks >> np.uint32(sh)) & np.uint32(0xFF)).astype(np.int64).sum(axis=(1, 3)) // (aa_res * aa_res)
+        out += (s_.astype(np.uint64) & np.uint64(0xFF)) << np.uint64(sh)
+    return out.astype(np.uint32)

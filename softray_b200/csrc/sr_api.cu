@@ -28,6 +28,8 @@ cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstan
                           int grid_blocks, cudaStream_t stream);
 int render_kernel_occupancy(int smem_bytes);
 cudaError_t measure_fma_peak(bool fp64, int sm_count, cudaStream_t stream, double* tflops);
+cudaError_t launch_resolve(const uint32_t* d_src, uint32_t* d_dst, int dst_w, int dst_h, int aa, int style, uint32_t background,
+                           cudaStream_t stream);
 }  // namespace sr
 
 using namespace sr;
@@ -943,6 +945,49 @@ extern "C" int softray_ipc_close(softray_ctx* ctx, void* d_ptr)
     if (!ctx || !d_ptr) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_ipc_close: NULL argument");
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     SR_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return SOFTRAY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// resolve: PostProcessImage + AntiAliasImage (Renderer.cs:819-898,937-978)
+// ---------------------------------------------------------------------------------------------
+static int check_resolve(softray_ctx* ctx, const void* src, const void* dst, int32_t w, int32_t h, int32_t aa, int32_t style)
+{
+    if (!ctx || !src || !dst) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_resolve: NULL argument");
+    if (w <= 0 || h <= 0 || aa < 1 || aa > 64 || (int64_t)w * aa > 65535 * 4 || (int64_t)h * aa > 65535 * 4)
+        return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_resolve: bad surface size or AntiAliasResolution");
+    if (style != SOFTRAY_STYLE_STANDARD && style != SOFTRAY_STYLE_COLOR_SHUFFLE && style != SOFTRAY_STYLE_NEGATIVE)
+        return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_resolve: the depth styles need the rasteriser's depth buffers");
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_resolve_device(softray_ctx* ctx, const uint32_t* d_src, int32_t w, int32_t h, int32_t aa, int32_t style,
+                                      uint32_t background, uint32_t* d_dst, void* stream)
+{
+    int rc = check_resolve(ctx, d_src, d_dst, w, h, aa, style);
+    if (rc != SOFTRAY_OK) return rc;
+    if (aa > 1 && d_src == d_dst) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_resolve: dst may alias src only when aa_res == 1");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    SR_CUDA(ctx, launch_resolve(d_src, d_dst, w, h, aa, style, background, stream ? static_cast<cudaStream_t>(stream) : ctx->stream));
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_resolve(softray_ctx* ctx, const uint32_t* src, int32_t w, int32_t h, int32_t aa, int32_t style,
+                               uint32_t background, uint32_t* dst)
+{
+    int rc = check_resolve(ctx, src, dst, w, h, aa, style);
+    if (rc != SOFTRAY_OK) return rc;
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n_dst = (size_t)w * (size_t)h, n_src = n_dst * (size_t)aa * (size_t)aa;
+    uint32_t *d_src = nullptr, *d_dst = nullptr;
+    SR_CUDA(ctx, cudaMalloc((void**)&d_src, n_src * sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc((void**)&d_dst, n_dst * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_src, src, n_src * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_resolve(d_src, d_dst, w, h, aa, style, background, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d_dst, n_dst * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_src); cudaFree(d_dst);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "softray_resolve");
     return SOFTRAY_OK;
 }
 

@@ -15,7 +15,7 @@ from .scene import FrameParams, MeshData, SceneDescHolder, SphereData
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libsoftray_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["sr_api.cu", "sr_render.cu", "sr_diag.cu", "sr_bvh.cpp"]
+SOURCES = ["sr_api.cu", "sr_render.cu", "sr_diag.cu", "sr_bvh.cpp", "sr_model3ds.cpp", "sr_resolve.cu"]
 HEADERS = ["sr_types.h", "sr_bvh.h", os.path.join("..", "..", "include", "softray_cuda.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
@@ -28,7 +28,8 @@ EXPORTS = [
     "softray_scene_create", "softray_scene_destroy", "softray_scene_fingerprint",
     "softray_render", "softray_render_device", "softray_instance_init", "softray_frame_defaults",
     "softray_device_alloc", "softray_device_free", "softray_ipc_export", "softray_ipc_open", "softray_ipc_close",
-    "softray_measure_fma_peak",
+    "softray_measure_fma_peak", "softray_model_load_3ds", "softray_model_get_mesh", "softray_model_destroy",
+    "softray_resolve", "softray_resolve_device",
 ]
 
 _lib = None
@@ -93,6 +94,12 @@ def load():
     L.softray_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.softray_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.softray_ipc_close.argtypes = [vp, vp]
+    L.softray_resolve.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, vp]
+    L.softray_resolve_device.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, vp, vp]
+    L.softray_model_load_3ds.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(vp)]
+    L.softray_model_get_mesh.argtypes = [vp, C.POINTER(abi.Mesh)]
+    L.softray_model_destroy.argtypes = [vp]
+    L.softray_model_destroy.restype = None
     if L.softray_abi_version() != abi.ABI_VERSION:
         raise RuntimeError("libsoftray_cuda.so ABI version mismatch")
     for which, name in enumerate(["mesh", "sphere", "scene_desc", "instance", "frame", "stats"]):
@@ -106,6 +113,24 @@ def _check(rc, ctx_handle, what):
     if rc != abi.OK:
         msg = load().softray_last_error(ctx_handle)
         raise SoftRayError(rc, f"{what}: {msg.decode('utf-8', 'replace') if msg else ''}")
+
+
+def load_3ds(data: bytes) -> MeshData:
+    """softray_model_load_3ds: a .3DS byte stream -> MeshData (Model.Load3ds + PostProcessGeometry +
+    per-triangle colour packing, in native code; no device needed)."""
+    L = load()
+    h = C.c_void_p()
+    _check(L.softray_model_load_3ds(data, len(data), C.byref(h)), None, "softray_model_load_3ds")
+    try:
+        m = abi.Mesh()
+        _check(L.softray_model_get_mesh(h, C.byref(m)), None, "softray_model_get_mesh")
+        nv, nt = m.n_verts, m.n_tris
+        verts = np.ctypeslib.as_array(m.verts_xyz, shape=(nv, 3)).copy() if nv else np.zeros((0, 3))
+        tris = np.ctypeslib.as_array(m.tri_vidx, shape=(nt, 3)).copy() if nt else np.zeros((0, 3), dtype=np.int32)
+        argb = np.ctypeslib.as_array(m.tri_argb, shape=(nt,)).copy() if nt else np.zeros((0,), dtype=np.uint32)
+        return MeshData(verts, tris, argb, np.array(list(m.bbox_min)), np.array(list(m.bbox_max)))
+    finally:
+        L.softray_model_destroy(h)
 
 
 class Context:
@@ -135,6 +160,23 @@ class Context:
         out = C.c_double()
         _check(load().softray_measure_fma_peak(self._h, int(bool(fp64)), C.byref(out)), self._h, "softray_measure_fma_peak")
         return out.value
+
+    def resolve(self, src, aa_res=1, style=0, background=0):
+        """softray_resolve: PostProcessImage + AntiAliasImage of a host (H*aa, W*aa) uint32 surface."""
+        src = np.ascontiguousarray(src, dtype=np.uint32)
+        k = max(int(aa_res), 1)              # (a bad aa_res is the library's to reject)
+        h, w = src.shape[0] // k, src.shape[1] // k
+        assert src.shape == (h * k, w * k)
+        dst = np.empty((h, w), dtype=np.uint32)
+        _check(load().softray_resolve(self._h, src.ctypes.data_as(C.c_void_p), w, h, int(aa_res), int(style),
+                                      int(background) & 0xFFFFFFFF, dst.ctypes.data_as(C.c_void_p)), self._h, "softray_resolve")
+        return dst
+
+    def resolve_device(self, d_src, d_dst, width, height, aa_res=1, style=0, background=0, stream=None):
+        """softray_resolve_device on raw device pointers (ints)."""
+        _check(load().softray_resolve_device(self._h, C.c_void_p(d_src), int(width), int(height), int(aa_res), int(style),
+                                             int(background) & 0xFFFFFFFF, C.c_void_p(d_dst),
+                                             C.c_void_p(stream) if stream else None), self._h, "softray_resolve_device")
 
     # IPC helpers for the peer-mapped framebuffer (multi-GPU gather fused into the render kernel)
     def device_alloc(self, nbytes):

@@ -326,3 +326,43 @@ def test_config3_full_size_band_invariance(lib, ctx):
         sc.render(p, pixels=px)
     assert (px == full["pixels"]).all()
     assert full["stats"].rays_secondary > 0 and full["stats"].hits_primary > 1_000_000
+
+
+# ------------------------------------------------------------------------------------------------
+# the step after the path: PostProcessImage + AntiAliasImage on the device
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("aa", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("style", [0, 1, 2])
+def test_resolve_matches_oracle(ctx, aa, style):
+    import oracle
+
+    rng = synth.SplitMix64(1000 + 10 * aa + style)
+    h, w = 37, 53                                            # ragged: not a multiple of the block shape
+    src = (rng.next_u64(h * aa * w * aa) & np.uint64(0xFFFFFFFF)).astype(np.uint32).reshape(h * aa, w * aa)
+    src[::3, ::5] = 0x00FF00FF                               # the 24-bit background colour itself
+    src[1::4, 2::7] |= 0xFF000000
+    got = ctx.resolve(src, aa_res=aa, style=style, background=0xFF00FF)
+    want = oracle.resolve(src, aa_res=aa, style=style, background=0xFF00FF)
+    assert np.array_equal(got, want)
+
+
+def test_resolve_of_a_supersampled_render_equals_antialiasimage(lib, ctx, obj_scene, obj_oracle):
+    """AntiAliasResolution = 2: the frame is traced at 2x the size, then box-filtered (Renderer.cs:366-410,937-978)."""
+    import oracle
+
+    p = scenario(resolution=128)
+    hi = obj_scene.render(p)["pixels"]
+    got = ctx.resolve(hi, aa_res=2)
+    want = oracle.resolve(obj_oracle.render(p)["pixels"], aa_res=2)
+    assert np.array_equal(got, want) and got.shape == (64, 64) and ((got >> 24) == 0xFF).all()
+
+
+def test_resolve_error_contracts(lib, ctx):
+    src = np.zeros((8, 8), dtype=np.uint32)
+    for kw in (dict(style=3), dict(style=5)):
+        with pytest.raises(lib.SoftRayError) as e:
+            ctx.resolve(src, **kw)
+        assert e.value.code == abi.E_UNSUPPORTED
+    with pytest.raises(lib.SoftRayError) as e:
+        ctx.resolve(src, aa_res=0)
+    assert e.value.code == abi.E_INVALID_ARG
