@@ -337,13 +337,13 @@ def test_resolve_matches_oracle(ctx, aa, style):
     import oracle
 
     rng = synth.SplitMix64(1000 + 10 * aa + style)
-    h, w = 37, 53                                            # ragged: not a multiple of the block shape
-    src = (rng.next_u64(h * aa * w * aa) & np.uint64(0xFFFFFFFF)).astype(np.uint32).reshape(h * aa, w * aa)
-    src[::3, ::5] = 0x00FF00FF                               # the 24-bit background colour itself
-    src[1::4, 2::7] |= 0xFF000000
-    got = ctx.resolve(src, aa_res=aa, style=style, background=0xFF00FF)
-    want = oracle.resolve(src, aa_res=aa, style=style, background=0xFF00FF)
-    assert np.array_equal(got, want)
+    for h, w in ((37, 53), (41, 132)):                       # ragged scalar path; 128-bit vector path (w % 4 == 0)
+        src = (rng.next_u64(h * aa * w * aa) & np.uint64(0xFFFFFFFF)).astype(np.uint32).reshape(h * aa, w * aa)
+        src[::3, ::5] = 0x00FF00FF                           # the 24-bit background colour itself
+        src[1::4, 2::7] |= 0xFF000000
+        got = ctx.resolve(src, aa_res=aa, style=style, background=0xFF00FF)
+        want = oracle.resolve(src, aa_res=aa, style=style, background=0xFF00FF)
+        assert np.array_equal(got, want), (h, w)
 
 
 def test_resolve_of_a_supersampled_render_equals_antialiasimage(lib, ctx, obj_scene, obj_oracle):
