@@ -541,6 +541,15 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
             ds.n_sphere_nodes = (int32_t)bvh.nodes.size();
             // the entry clip works on the padded bounds
             for (int k = 0; k < 3; k++) { ds.sph_bmin[k] = lo[k] - (double)pad; ds.sph_bmax[k] = hi[k] + (double)pad; }
+            std::vector<float4> filt((size_t)desc->n_spheres);
+            for (int32_t k = 0; k < desc->n_spheres; k++) {
+                const SphereRec& r = ordered[(size_t)k];
+                filt[(size_t)k] = make_float4((float)r.cx, (float)r.cy, (float)r.cz, (float)r.r);
+            }
+            rc = upload(sc, filt, &ds.sph_filt);
+            if (rc != SOFTRAY_OK) return rc;
+            for (int k = 0; k < 3; k++) { ds.sph_fmin[k] = round_down(ds.sph_bmin[k]); ds.sph_fmax[k] = round_up(ds.sph_bmax[k]); }
+            ds.sph_scale = round_up(max_abs3(ds.sph_bmin, ds.sph_bmax));
         }
     }
     if (!meshes.empty()) {

@@ -477,8 +477,10 @@ __device__ __forceinline__ int fray_setup(const DevMesh& m, int subdivision, d3 
 // t0 <= (exact entry into the root box), computed in FP64 and then rounded, so that every FP32 operand
 // is of the order of the mesh whatever the distance of the camera; tau = t - t0.
 // 0: the ray surely misses the root box (no hit), 1: traverse, 2: cannot tell.
-__device__ __forceinline__ int fray_setup_fwd(const DevMesh& m, int subdivision, d3 s, d3 dir, FRay* r, double* t0_out)
+__device__ __forceinline__ int fray_setup_box(const float* __restrict__ bmin, const float* __restrict__ bmax, float scale,
+                                              int subdivision, d3 s, d3 dir, FRay* r, double* t0_out)
 {
+    struct { const float* fmin; const float* fmax; float scale; } m = {bmin, bmax, scale};
     const float sx = __double2float_rn(s.x), sy = __double2float_rn(s.y), sz = __double2float_rn(s.z);
     r->gx = __double2float_rn(dir.x); r->gy = __double2float_rn(dir.y); r->gz = __double2float_rn(dir.z);
     const float agx = fabsf(r->gx), agy = fabsf(r->gy), agz = fabsf(r->gz);
@@ -518,6 +520,11 @@ __device__ __forceinline__ int fray_setup_fwd(const DevMesh& m, int subdivision,
     r->tmax_lo = 1e30f;
     r->tcull = r->tmax_hi * 1.00002f + 1e-6f;
     return 1;
+}
+
+__device__ __forceinline__ int fray_setup_fwd(const DevMesh& m, int subdivision, d3 s, d3 dir, FRay* r, double* t0_out)
+{
+    return fray_setup_box(m.fmin, m.fmax, m.scale, subdivision, s, dir, r, t0_out);
 }
 
 __device__ __forceinline__ bool fslab(const FRay& r, float lox, float loy, float loz, float hix, float hiy, float hiz,
@@ -664,6 +671,110 @@ __device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// FP32 filter for spheres (Sphere.IntersectRay, Sphere.cs:152-219).  The ray is P(tau) = o + g tau with
+// g = dir rounded (not normalised); L = |g|.  In DISTANCE units (the unit of a sphere's rayFrac, SURVEY
+// App. A #3):  proj = (o - c).g / L,  term = proj^2 - |o - c|^2 + r^2,  d = -proj -+ sqrt(term),
+// rayFrac = T0 + d  with T0 = (distance from the ray start to the anchor o).
+// Bounds (u = 2^-24):  |o_k - c_k| error e_o = 3u (|o|_inf + V);  E_p = (e_o |g|_1 + 5u |o-c|_1 |g|_inf) / L + 6u |proj|;
+// E_t = 2|proj| E_p + E_p^2 + 2 |o-c|_1 e_o + 3 e_o^2 + 8u (proj^2 + |o-c|^2 + r^2);
+// E_root = E_t / (2 sqrt(term - E_t)) + 2u root;  E_d = E_p + E_root + 2u (|proj| + root) + 4u T0.
+// 0: surely missed; 1: surely hit from outside (rayFrac = T0 + d1 within [*lo, *hi]); 2: cannot tell.
+// ---------------------------------------------------------------------------------------------
+struct SRay { float inv_len, T0; };
+
+__device__ __forceinline__ int sphere_filter(const float4* __restrict__ rec, const FRay& r, const SRay& sr, float V, float* lo,
+                                             float* hi)
+{
+    const float4 q = __ldg(rec);
+    const float ox = r.ox - q.x, oy = r.oy - q.y, oz = r.oz - q.z;
+    const float e_o = (3.0f * kU) * (r.oinf + V);
+    const float o1 = fabsf(ox) + fabsf(oy) + fabsf(oz);
+    const float proj = __fmaf_rn(oz, r.gz, __fmaf_rn(oy, r.gy, ox * r.gx)) * sr.inv_len;
+    const float e_p = (e_o * r.g1 + (5.0f * kU) * o1 * r.ginf) * sr.inv_len * 1.01f + (6.0f * kU) * fabsf(proj);
+    const float oo = __fmaf_rn(oz, oz, __fmaf_rn(oy, oy, ox * ox));
+    const float rr = q.w * q.w;
+    const float term = __fmaf_rn(proj, proj, rr - oo);
+    const float e_t = 2.0f * fabsf(proj) * e_p + e_p * e_p + 2.0f * o1 * e_o + 3.0f * e_o * e_o +
+                      (8.0f * kU) * (proj * proj + oo + rr);
+    *lo = 0.0f; *hi = 0.0f;
+    if (term + e_t < 1e-10f) return 0;                                   // `term < EPSILON` (Sphere.cs:176)
+    const float term_lo = term - e_t;
+    if (!(term_lo > 1.0001e-10f)) return 2;
+    const float root = sqrtf(term);
+    const float e_root = __fdividef(e_t, 2.0f * sqrtf(term_lo)) * 1.01f + (2.0f * kU) * root;
+    const float e_d = e_p + e_root + (2.0f * kU) * (fabsf(proj) + root) + (4.0f * kU) * sr.T0;
+    const float d1 = -proj - root, d2 = -proj + root;
+    if (sr.T0 + d2 + e_d < 0.0f) return 0;                               // the whole sphere lies behind the start
+    const float rf = sr.T0 + d1;
+    if (rf - e_d > 0.0f) { *lo = rf - e_d; *hi = rf + e_d; return 1; }  // entering from outside: rayFrac = f1
+    return 2;                                                            // start inside / on the sphere, NaN, ...
+}
+
+// The sphere part of rootGeometry for one ray.  ANY: is there a sphere with rayFrac <= 1.0 (shadow rays)?
+// returns 0 no, 1 yes, 2 cannot tell.  !ANY: nearest sphere -> candidates, as walk_filter_closest.
+// In both cases list[0..*n_list) names the spheres the exact arithmetic has to look at (> kMaxCand: all).
+template <bool ANY>
+__device__ __forceinline__ int spheres_filter(const DevScene& sc, d3 s, d3 dir, int* list, int* n_list, unsigned int* nv_out,
+                                              unsigned int* nf_out, int* stack)
+{
+    FRay r; double t0;
+    *n_list = 0;
+    int st = fray_setup_box(sc.sph_fmin, sc.sph_fmax, sc.sph_scale, 0, s, dir, &r, &t0);
+    if (st != 1) return st == 0 ? 0 : 2;
+    const float len = sqrtf(r.gx * r.gx + r.gy * r.gy + r.gz * r.gz);
+    SRay sr; sr.inv_len = __fdiv_rn(1.0f, len); sr.T0 = (float)t0 * len;
+    if (ANY) {
+        // a sphere's rayFrac is at least the distance to its (padded) box: beyond 1.0 nothing can occlude
+        if (sr.T0 * (1.0f - 8.0f * kU) > 1.0f) return 0;
+        r.tcull = fminf(r.tcull, (1.0f - sr.T0) * sr.inv_len * 1.0001f + 1e-6f);
+    }
+    float best_hi = 1e30f;
+    bool occluded = false;
+    int n = 0, c0 = -1, c1 = -1, c2 = -1, c3 = -1;
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    unsigned int nf = 0;
+    *nv_out += walk_bvh(
+        sc.sphere_nodes, stack,
+        [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float* t) {
+            return fslab(r, lox, loy, loz, hix, hiy, hiz, t);
+        },
+        [&](int first, int count) {
+            for (int i = 0; i < count; i++) {
+                nf++;
+                float lo, hi;
+                const int res = sphere_filter(sc.sph_filt + first + i, r, sr, sc.sph_scale, &lo, &hi);
+                if (res == 0) continue;
+                if (ANY) {
+                    if (res == 1 && hi <= 1.0f) { occluded = true; return true; }
+                    if (res == 1 && lo > 1.0f) continue;                  // hit, but further than 1.0 from the start
+                } else if (res == 1 && lo > best_hi) {
+                    continue;                                             // surely behind a sure hit
+                }
+                if (n == 0) { c0 = first + i; l0 = lo; } else if (n == 1) { c1 = first + i; l1 = lo; }
+                else if (n == 2) { c2 = first + i; l2 = lo; } else if (n == 3) { c3 = first + i; l3 = lo; }
+                n++;
+                if (!ANY && res == 1 && hi < best_hi) {
+                    best_hi = hi;
+                    r.tcull = fminf(r.tcull, (hi - sr.T0) * sr.inv_len * 1.0001f + 1e-6f);
+                }
+            }
+            return false;
+        });
+    *nf_out += nf;
+    if (ANY && occluded) return 1;
+    if (n == 0) return 0;
+    if (n > kMaxCand) { *n_list = n; return 2; }
+    // candidates that can still beat (or tie) the best sure hit; an undecided candidate has lo = 0
+    const int cs[4] = {c0, c1, c2, c3};
+    const float ls[4] = {l0, l1, l2, l3};
+    int m = 0;
+    for (int j = 0; j < n; j++)
+        if (ANY || ls[j] <= best_hi) list[m++] = cs[j];
+    *n_list = m;
+    return 2;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Shadow bundles (DESIGN.md "Shadow bundles").  The softShadowQuality rays of one shading point all
 // end in the same point `end` and start inside the ball of radius rho around the light: they lie in
 // the cone  { end + tau * g : 0 <= tau <= 1, |g - g_c| <= rho },  g_c = light - end.  One conservative
@@ -791,8 +902,20 @@ struct Hit {
 constexpr double kNoHit = 1.7976931348623157e308;   // double.MaxValue (GeometryCollection.cs:48)
 
 // Exact (reference arithmetic) nearest sphere / nearest triangle.
-__device__ __noinline__ void spheres_closest_exact(const DevScene& sc, d3 s, d3 dirn, BestPrim* bs, XCounters* c)
+__device__ __noinline__ void spheres_closest_exact(const DevScene& sc, d3 s, d3 dirn, const int* list, int n_list, BestPrim* bs,
+                                                   XCounters* c)
 {
+    if (n_list > 0) {       // only the spheres the filter could not rule out
+        for (int j = 0; j < n_list; j++) {
+            const int k = list[j];
+            double rf;
+            c->prim_tests++; c->sphere_tests++;
+            if (!sphere_intersect(sc.spheres + k, s, dirn, &rf)) continue;
+            const int index = __ldg(reinterpret_cast<const int*>(sc.spheres + k) + 11);
+            if (rf < bs->rf || (rf == bs->rf && index < bs->index)) { bs->rf = rf; bs->k = k; bs->index = index; }
+        }
+        return;
+    }
     if (sc.sphere_nodes) {
         double te;
         if (entry_clip(sc.sph_bmin, sc.sph_bmax, 0.0, s, dirn, &te)) {
@@ -844,7 +967,27 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
     d3 dirn = dir;
     if (sc.n_spheres > 0) {
         dirn = vnormalise(dir);                          // Sphere.cs:160
-        spheres_closest_exact(sc, s, dirn, &bs, c);
+        int known = 2;                                   // 0: surely no sphere; 2: look at list (or at all of them)
+        int list[kMaxCand]; int n_list = 0;
+        if (filter_mode != 1 && sc.sphere_nodes != nullptr) {
+            unsigned int nv = 0, nf = 0;
+            known = spheres_filter<false>(sc, s, dir, list, &n_list, &nv, &nf, c->stack);
+            c->node_visits += nv; c->filter_tests += nf;
+        }
+        const bool listed = known == 2 && n_list >= 1 && n_list <= kMaxCand;
+        if (filter_mode == 2) {
+            spheres_closest_exact(sc, s, dirn, nullptr, 0, &bs, c);
+            bool in_list = bs.k < 0 || !listed;
+            for (int j = 0; listed && j < n_list; j++) in_list = in_list || list[j] == bs.k;
+            if ((known == 0 && bs.k >= 0) || !in_list) c->filter_mismatch++;
+            if (known == 2 && n_list != 1) c->filter_unsure++;
+        } else if (listed) {
+            if (n_list > 1) c->filter_unsure++;
+            spheres_closest_exact(sc, s, dirn, list, n_list, &bs, c);
+        } else if (known == 2) {
+            if (filter_mode != 1 && sc.sphere_nodes != nullptr) c->filter_unsure++;
+            spheres_closest_exact(sc, s, dirn, nullptr, 0, &bs, c);
+        }
     }
     // --- mesh ---
     BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
@@ -942,11 +1085,19 @@ __device__ __noinline__ bool occluded_mesh(const DevMesh& m, int subdivision, d3
     return scan<0, true>(m.tris, m.n_tris, ts, dir, limit, offset, &dummy, c);
 }
 
-__device__ __noinline__ bool occluded_spheres(const DevScene& sc, d3 s, d3 dir, XCounters* c)
+__device__ __noinline__ bool occluded_spheres(const DevScene& sc, d3 s, d3 dir, const int* list, int n_list, XCounters* c)
 {
     BestPrim dummy; dummy.rf = kNoHit; dummy.k = -1; dummy.index = 0;
     if (sc.n_spheres <= 0) return false;
     const d3 dirn = vnormalise(dir);
+    if (n_list > 0) {       // only the spheres the filter could not decide
+        for (int j = 0; j < n_list; j++) {
+            double rf;
+            c->prim_tests++; c->sphere_tests++;
+            if (sphere_intersect(sc.spheres + list[j], s, dirn, &rf) && rf <= 1.0) return true;
+        }
+        return false;
+    }
     if (sc.sphere_nodes) {
         double te;
         if (entry_clip(sc.sph_bmin, sc.sph_bmax, 0.0, s, dirn, &te) && te <= 1.0) {
@@ -1010,7 +1161,7 @@ __device__ __forceinline__ bool occluded_exact(const DevScene& sc, const DevInst
                                                d3 start, d3 dir, const int* list, int n_list, XCounters* c)
 {
     if (occluded_mesh(m, subdivision, start, dir, list, n_list, c)) return true;
-    return in.sph_can_shadow && occluded_spheres(sc, start, dir, c);
+    return in.sph_can_shadow && occluded_spheres(sc, start, dir, nullptr, 0, c);
 }
 
 __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const DevScene& sc, const DevInstance& in,
@@ -1067,7 +1218,25 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
                 } else {
                     occ = res == 1;
                 }
-                if (!occ && in.sph_can_shadow) occ = occluded_spheres(sc, start, dir, xc);
+                if (!occ && in.sph_can_shadow) {
+                    int sres = 2;
+                    int sl[kMaxCand]; int nsl = 0;
+                    if (sc.sphere_nodes != nullptr) {
+                        unsigned int nv = 0, nf = 0;
+                        sres = spheres_filter<true>(sc, start, dir, sl, &nsl, &nv, &nf, c->stack);
+                        c->node_visits += nv; c->filter_tests += nf;
+                    }
+                    if (nsl > kMaxCand) nsl = 0;
+                    if (f.filter_mode == 2) {
+                        occ = occluded_spheres(sc, start, dir, nullptr, 0, xc);
+                        if ((sres == 0 && occ) || (sres == 1 && !occ)) c->filter_mismatch++;
+                        if (sres == 2 && nsl > 0 && occluded_spheres(sc, start, dir, sl, nsl, xc) != occ) c->filter_mismatch++;
+                    } else if (sres == 2) {
+                        occ = occluded_spheres(sc, start, dir, sl, nsl, xc);
+                    } else {
+                        occ = sres == 1;
+                    }
+                }
             } else {
                 occ = occluded_exact(sc, in, m, f.subdivision, start, dir, nullptr, 0, xc);
             }

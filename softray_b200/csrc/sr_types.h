@@ -2,6 +2,7 @@
 // (sr_api.cu, sr_bvh.cpp) and the kernels (sr_render.cu).  See DESIGN.md "Data layout in HBM".
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 #if defined(__CUDACC__)
 #define SR_HD __host__ __device__
@@ -91,6 +92,10 @@ struct DevScene {
     const BvhNode*   sphere_nodes;
     int32_t n_spheres;          int32_t n_sphere_nodes;
     double  sph_bmin[3], sph_bmax[3];   // bounds of all spheres (traversal entry clip only)
+    const float4*    sph_filt;          // FP32 filter records (cx, cy, cz, r), same order as spheres; BVH mode only
+    float   sph_fmin[3], sph_fmax[3];   // sph_bmin / sph_bmax rounded outward to FP32
+    float   sph_scale;                  // largest |coordinate| of the sphere bounds, rounded up
+    int32_t _pad2;
 };
 
 struct DevInstance {
