@@ -1357,7 +1357,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
 }
 
 #ifndef SR_MIN_BLOCKS
-#define SR_MIN_BLOCKS 4
+#define SR_MIN_BLOCKS 6     // 6 x 128 threads x 85 registers: measured best over the four big configs (profiles/)
 #endif
 __global__ void __launch_bounds__(128, SR_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevScene sc, const DevInstance* __restrict__ g_insts, const double* __restrict__ g_offsets,
