@@ -339,7 +339,7 @@ def main():
         h2d = 288 * len(frame.instances) + (24 * frame.shadow_samples if frame.shadows else 0)
         e2e = {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": W * H * 4,
-               "note": "softray_render (C ABI) with a pinned host framebuffer; the scene is resident "
+               "note": "softray_render (C ABI) with a pinned host framebuffer, which the kernel writes directly over PCIe (zero-copy stores: the D2H bytes leave the GPU while tracing continues); the scene is resident "
                        "(uploaded once by softray_scene_create, like the reference caches its geometry)"}
 
     # ---- roofline of the render kernel: FP issue (branchy FP32 search + FP64 reference arithmetic; not

@@ -790,6 +790,16 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     return SOFTRAY_OK;
 }
 
+// device-side alias of a page-locked host buffer, or nullptr if `host` is pageable / not mappable
+template <typename T>
+T* zero_copy_pointer(T* host)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return nullptr;
+    return static_cast<T*>(a.devicePointer);
+}
+
 int enqueue_frame(softray_ctx* ctx, const softray_scene* scene, const Prepared& p, uint32_t* d_pixels, int32_t* d_ids,
                   cudaStream_t stream, bool timed)
 {
@@ -871,31 +881,42 @@ extern "C" int softray_render(softray_ctx* ctx, const softray_scene* scene, cons
     int rc = prepare_frame(ctx, scene, frame, &p);
     if (rc != SOFTRAY_OK) return rc;
     const size_t n_px = (size_t)frame->width * (size_t)frame->height;
-    if (ctx->fb_capacity < n_px) {
-        cudaFree(ctx->d_pixels); ctx->d_pixels = nullptr; ctx->fb_capacity = 0;
-        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_pixels, n_px * sizeof(uint32_t)));
-        ctx->fb_capacity = n_px;
-    }
-    if (hit_ids && ctx->ids_capacity < n_px) {
-        cudaFree(ctx->d_ids); ctx->d_ids = nullptr; ctx->ids_capacity = 0;
-        SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_ids, n_px * sizeof(int32_t)));
-        ctx->ids_capacity = n_px;
-    }
+    // A page-locked (CUDA-registered / cudaHostAlloc'd) caller buffer is mapped into the device's address
+    // space: the kernel then stores finished pixels straight into it over PCIe, overlapped with tracing,
+    // and there is no device framebuffer and no D2H copy.  Pageable memory takes the staging path below.
+    uint32_t* zc_pixels = zero_copy_pointer(pixels_argb);
+    int32_t* zc_ids = hit_ids ? zero_copy_pointer(hit_ids) : nullptr;
+    const bool zero_copy = zc_pixels != nullptr && (!hit_ids || zc_ids != nullptr) && !env_int("SOFTRAY_NO_ZERO_COPY", 0);
     cudaStream_t s = ctx->stream;
-    rc = enqueue_frame(ctx, scene, p, ctx->d_pixels, hit_ids ? ctx->d_ids : nullptr, s, true);
-    if (rc != SOFTRAY_OK) return rc;
-    // read back exactly the rows that were rendered; banded frames copy each
-    // band of this rank separately so the caller's other rows stay untouched
-    const size_t W = (size_t)frame->width;
-    const bool banded = p.f.band_count > 1;
-    const int bh = banded ? p.f.band_height : (p.end_row - p.start_row + 1);
-    for (int top = p.start_row, b = 0; top <= p.end_row; top += bh, b++) {
-        if (banded && b % p.f.band_count != p.f.band_index) continue;
-        const int last = top + bh - 1 > p.end_row ? p.end_row : top + bh - 1;
-        const size_t off = (size_t)top * W, cnt = (size_t)(last - top + 1) * W;
-        SR_CUDA(ctx, cudaMemcpyAsync(pixels_argb + off, ctx->d_pixels + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        if (hit_ids)
-            SR_CUDA(ctx, cudaMemcpyAsync(hit_ids + off, ctx->d_ids + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (zero_copy) {
+        rc = enqueue_frame(ctx, scene, p, zc_pixels, zc_ids, s, true);
+        if (rc != SOFTRAY_OK) return rc;
+    } else {
+        if (ctx->fb_capacity < n_px) {
+            cudaFree(ctx->d_pixels); ctx->d_pixels = nullptr; ctx->fb_capacity = 0;
+            SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_pixels, n_px * sizeof(uint32_t)));
+            ctx->fb_capacity = n_px;
+        }
+        if (hit_ids && ctx->ids_capacity < n_px) {
+            cudaFree(ctx->d_ids); ctx->d_ids = nullptr; ctx->ids_capacity = 0;
+            SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_ids, n_px * sizeof(int32_t)));
+            ctx->ids_capacity = n_px;
+        }
+        rc = enqueue_frame(ctx, scene, p, ctx->d_pixels, hit_ids ? ctx->d_ids : nullptr, s, true);
+        if (rc != SOFTRAY_OK) return rc;
+        // read back exactly the rows that were rendered; banded frames copy each
+        // band of this rank separately so the caller's other rows stay untouched
+        const size_t W = (size_t)frame->width;
+        const bool banded = p.f.band_count > 1;
+        const int bh = banded ? p.f.band_height : (p.end_row - p.start_row + 1);
+        for (int top = p.start_row, b = 0; top <= p.end_row; top += bh, b++) {
+            if (banded && b % p.f.band_count != p.f.band_index) continue;
+            const int last = top + bh - 1 > p.end_row ? p.end_row : top + bh - 1;
+            const size_t off = (size_t)top * W, cnt = (size_t)(last - top + 1) * W;
+            SR_CUDA(ctx, cudaMemcpyAsync(pixels_argb + off, ctx->d_pixels + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            if (hit_ids)
+                SR_CUDA(ctx, cudaMemcpyAsync(hit_ids + off, ctx->d_ids + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        }
     }
     SR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
     if (stats) {

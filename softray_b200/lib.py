@@ -6,6 +6,7 @@ load time, a missing CUDA device makes Context() raise SoftRayError(E_NO_DEVICE)
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -143,9 +144,12 @@ class Context:
             self._h = C.c_void_p()
             _check(rc, None, "softray_create")
         self.device = int(device)
+        self._scenes = weakref.WeakSet()     # scenes hold device memory of this context: they go first
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
+            for sc in list(getattr(self, "_scenes", ())):
+                sc.close()
             load().softray_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -210,6 +214,7 @@ class Scene:
         self._h = C.c_void_p()
         _check(load().softray_scene_create(ctx._h, C.byref(self.holder.desc), C.byref(self._h)), ctx._h,
                "softray_scene_create")
+        ctx._scenes.add(self)
 
     def fingerprint(self):
         out = C.c_uint64()

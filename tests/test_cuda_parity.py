@@ -366,3 +366,18 @@ def test_resolve_error_contracts(lib, ctx):
     with pytest.raises(lib.SoftRayError) as e:
         ctx.resolve(src, aa_res=0)
     assert e.value.code == abi.E_INVALID_ARG
+
+
+def test_pinned_host_framebuffer_is_written_by_the_kernel_itself(obj_scene):
+    """softray_render stores straight into a page-locked caller buffer (no device framebuffer, no D2H copy);
+    a pageable buffer goes through the staging copy.  Same pixels, same ids, and only the requested rows."""
+    import torch
+
+    p = scenario(resolution=160, shadows=True, shadow_samples=8, start_row=11, end_row=140)
+    want = obj_scene.render(p, want_ids=True, pixels=np.full((160, 160), 0xABCDEF01, dtype=np.uint32),
+                            ids=np.full((160, 160), 777, dtype=np.int32))
+    px = torch.full((160, 160), 0xABCDEF01 - (1 << 32), dtype=torch.int32).pin_memory()
+    ids = torch.full((160, 160), 777, dtype=torch.int32).pin_memory()
+    got = obj_scene.render(p, want_ids=True, pixels=px.numpy().view(np.uint32), ids=ids.numpy())
+    assert np.array_equal(got["pixels"], want["pixels"]) and np.array_equal(got["ids"], want["ids"])
+    assert (got["pixels"][:11] == 0xABCDEF01).all() and (got["pixels"][141:] == 0xABCDEF01).all()
