@@ -15,7 +15,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/softray_cuda.h"
@@ -229,12 +232,31 @@ void area_light_offsets(int32_t seed, int n, double* out)
     }
 }
 
+// layout fingerprint: FNV-1a over 64-bit words (the tail bytewise) -- every uploaded byte takes part
 inline void fnv(uint64_t* h, const void* data, size_t n)
 {
     const unsigned char* p = static_cast<const unsigned char*>(data);
     uint64_t x = *h;
-    for (size_t i = 0; i < n; i++) { x ^= p[i]; x *= 1099511628211ull; }
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; std::memcpy(&w, p + i, 8); x ^= w; x *= 1099511628211ull; }
+    for (; i < n; i++) { x ^= p[i]; x *= 1099511628211ull; }
     *h = x;
+}
+
+// run fn(begin, end) over [0, n) on several host threads (per-element work only: no ordering effects)
+template <typename F>
+void parallel_for(int64_t n, F fn)
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = n >= 100000 ? (int)std::min<unsigned>(hw ? hw : 1u, 32u) : 1;
+    if (nt <= 1) { fn((int64_t)0, n); return; }
+    std::vector<std::thread> pool;
+    const int64_t chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        const int64_t b = t * chunk, e = std::min<int64_t>(n, b + chunk);
+        if (b < e) pool.emplace_back([=]() { fn(b, e); });
+    }
+    for (auto& th : pool) th.join();
 }
 
 // upload one host array; records the allocation and folds the bytes into the layout fingerprint
@@ -444,23 +466,27 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
             return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: mesh arrays missing");
         std::vector<TriRec> recs((size_t)m.n_tris);
         std::vector<PrimBounds> bounds((size_t)m.n_tris);
-        for (int32_t i = 0; i < m.n_tris; i++) {
-            hv v[3];
-            for (int k = 0; k < 3; k++) {
-                const int32_t vi = m.tri_vidx[3 * (size_t)i + k];
-                if (vi < 0 || vi >= m.n_verts) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: vertex index out of range");
-                v[k] = hmk(m.verts_xyz[3 * (size_t)vi], m.verts_xyz[3 * (size_t)vi + 1], m.verts_xyz[3 * (size_t)vi + 2]);
-                // SpatialSubdivision ctor: every vertex inside the bounding box (SpatialSubdivision.cs:285-295)
-                if (!box_contains(m.bbox_min, m.bbox_max, v[k]))
-                    return fail(ctx, SOFTRAY_E_VERTEX_OUTSIDE_BBOX, "A triangle vertex is outside the bounding box");
+        std::atomic<int> bad(0);            // 1: vertex index out of range, 2: vertex outside the bounding box
+        parallel_for(m.n_tris, [&](int64_t i0, int64_t i1) {
+            for (int64_t i = i0; i < i1; i++) {
+                hv v[3];
+                for (int k = 0; k < 3; k++) {
+                    const int32_t vi = m.tri_vidx[3 * (size_t)i + k];
+                    if (vi < 0 || vi >= m.n_verts) { bad = 1; return; }
+                    v[k] = hmk(m.verts_xyz[3 * (size_t)vi], m.verts_xyz[3 * (size_t)vi + 1], m.verts_xyz[3 * (size_t)vi + 2]);
+                    // SpatialSubdivision ctor: every vertex inside the bounding box (SpatialSubdivision.cs:285-295)
+                    if (!box_contains(m.bbox_min, m.bbox_max, v[k])) { int z = 0; bad.compare_exchange_strong(z, 2); return; }
+                }
+                make_tri_rec(&recs[(size_t)i], v[0], v[1], v[2], m.tri_argb[i], (int32_t)i);
+                PrimBounds& b = bounds[(size_t)i];
+                const double xs[3] = {v[0].x, v[1].x, v[2].x}, ys[3] = {v[0].y, v[1].y, v[2].y}, zs[3] = {v[0].z, v[1].z, v[2].z};
+                b.lo[0] = round_down(std::fmin(xs[0], std::fmin(xs[1], xs[2]))); b.hi[0] = round_up(std::fmax(xs[0], std::fmax(xs[1], xs[2])));
+                b.lo[1] = round_down(std::fmin(ys[0], std::fmin(ys[1], ys[2]))); b.hi[1] = round_up(std::fmax(ys[0], std::fmax(ys[1], ys[2])));
+                b.lo[2] = round_down(std::fmin(zs[0], std::fmin(zs[1], zs[2]))); b.hi[2] = round_up(std::fmax(zs[0], std::fmax(zs[1], zs[2])));
             }
-            make_tri_rec(&recs[(size_t)i], v[0], v[1], v[2], m.tri_argb[i], i);
-            PrimBounds& b = bounds[(size_t)i];
-            const double xs[3] = {v[0].x, v[1].x, v[2].x}, ys[3] = {v[0].y, v[1].y, v[2].y}, zs[3] = {v[0].z, v[1].z, v[2].z};
-            b.lo[0] = round_down(std::fmin(xs[0], std::fmin(xs[1], xs[2]))); b.hi[0] = round_up(std::fmax(xs[0], std::fmax(xs[1], xs[2])));
-            b.lo[1] = round_down(std::fmin(ys[0], std::fmin(ys[1], ys[2]))); b.hi[1] = round_up(std::fmax(ys[0], std::fmax(ys[1], ys[2])));
-            b.lo[2] = round_down(std::fmin(zs[0], std::fmin(zs[1], zs[2]))); b.hi[2] = round_up(std::fmax(zs[0], std::fmax(zs[1], zs[2])));
-        }
+        });
+        if (bad == 1) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: vertex index out of range");
+        if (bad == 2) return fail(ctx, SOFTRAY_E_VERTEX_OUTSIDE_BBOX, "A triangle vertex is outside the bounding box");
         DevMesh& dm = meshes[(size_t)mi];
         std::memset(&dm, 0, sizeof dm);
         dm.n_tris = m.n_tris;
@@ -482,14 +508,19 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
             build_bvh(bounds, traversal_pad(max_abs3(m.bbox_min, m.bbox_max)), kMaxLeafPrims, sah_isect_cost(kTriIsectCost), &bvh);
             if (bvh.depth >= kStackEntries) return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_scene_create: BVH too deep");
             std::vector<TriRec> ordered((size_t)m.n_tris);
-            for (int32_t k = 0; k < m.n_tris; k++) ordered[(size_t)k] = recs[(size_t)bvh.order[(size_t)k]];
+            std::vector<TriFilt> filt((size_t)m.n_tris);
+            parallel_for(m.n_tris, [&](int64_t k0, int64_t k1) {
+                for (int64_t k = k0; k < k1; k++) {
+                    ordered[(size_t)k] = recs[(size_t)bvh.order[(size_t)k]];
+                    make_tri_filt(&filt[(size_t)k], ordered[(size_t)k]);
+                }
+            });
+            std::vector<TriRec>().swap(recs);
             int rc = upload(sc, ordered, &dm.tris);
             if (rc != SOFTRAY_OK) return rc;
             rc = upload(sc, bvh.nodes, &dm.nodes);
             if (rc != SOFTRAY_OK) return rc;
             dm.n_nodes = (int32_t)bvh.nodes.size();
-            std::vector<TriFilt> filt((size_t)m.n_tris);
-            for (int32_t k = 0; k < m.n_tris; k++) make_tri_filt(&filt[(size_t)k], ordered[(size_t)k]);
             rc = upload(sc, filt, &dm.filt);
             if (rc != SOFTRAY_OK) return rc;
         }
