@@ -34,7 +34,20 @@ BYTES = dict(node=64, tri=128, tri_filter=64, sphere=48, pixel=4)   # what ONE v
 def workload(name, scale=1.0):
     from softray_b200 import synth
 
-    if name == "config2":
+    if name == "config1":
+        # configs[0]: the reference's own test model through the native loader, 512x512, Lambert
+        import numpy as np
+
+        from softray_b200 import lib
+        from softray_b200.scene import FrameParams
+
+        fx = np.load(os.path.join(ROOT, "tests", "golden", "reference_fixtures.npz"))
+        m = [lib.load_3ds(fx["model/obj.3ds"].tobytes())]
+        s = None
+        f = FrameParams(width=int(512 * scale), height=int(512 * scale), instances=[synth.camera(1.0)], background=synth.BACKGROUND,
+                        shading=True, specular_lighting=False, shadows=False)
+        desc = "configs[0]: Raytracer/obj.3DS (152 triangles) via the native 3DS loader, 512x512, 1 spp, primary rays + Lambert"
+    elif name == "config2":
         m, s, f = synth.config2(width=int(1920 * scale), height=int(1080 * scale))
         desc = "configs[1]: procedural 1000-sphere scene in a 12-triangle room, 1920x1080, 1 spp, Phong + 100 soft-shadow rays per hit"
     elif name == "config2-hard":

@@ -381,3 +381,14 @@ def test_pinned_host_framebuffer_is_written_by_the_kernel_itself(obj_scene):
     got = obj_scene.render(p, want_ids=True, pixels=px.numpy().view(np.uint32), ids=ids.numpy())
     assert np.array_equal(got["pixels"], want["pixels"]) and np.array_equal(got["ids"], want["ids"])
     assert (got["pixels"][:11] == 0xABCDEF01).all() and (got["pixels"][141:] == 0xABCDEF01).all()
+
+
+def test_config1_full_size_against_oracle(lib, ctx, fixtures, obj_oracle):
+    """configs[0] as named: obj.3DS through the NATIVE loader, 512x512, 1 spp, primary rays + Lambert
+    (specularLighting = false) -- every pixel and hit id against the oracle."""
+    mesh = lib.load_3ds(fixtures["model/obj.3ds"].tobytes())
+    p = scenario(resolution=512, specular_lighting=False)
+    got = lib.Scene(ctx, [mesh]).render(p, want_ids=True)
+    want = obj_oracle.render(p, want_ids=True, want_aux=True)
+    assert_parity(got, want, what="config1 512x512")
+    assert got["stats"].rays_primary == 512 * 512 and got["stats"].rays_shadow == 0
