@@ -392,3 +392,30 @@ def test_config1_full_size_against_oracle(lib, ctx, fixtures, obj_oracle):
     want = obj_oracle.render(p, want_ids=True, want_aux=True)
     assert_parity(got, want, what="config1 512x512")
     assert got["stats"].rays_primary == 512 * 512 and got["stats"].rays_shadow == 0
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_random_soups_and_spheres_against_oracle(lib, ctx, seed):
+    """Fuzz: random intersecting triangle soups + random spheres, random camera / light / flags, every
+    pixel and hit id against the oracle (whose mesh path is the reference's kd-style tree)."""
+    import oracle
+
+    rng = synth.SplitMix64(seed)
+    n = [60, 400, 2500, 9000][seed % 4]
+    size = [0.4, 0.15, 0.06, 0.03][seed % 4]
+    c = rng.uniform(3 * n).reshape(n, 3) - 0.5
+    e = (rng.uniform(6 * n).reshape(n, 2, 3) - 0.5) * size
+    v = np.concatenate([c, c + e[:, 0], c + e[:, 1]]).clip(-0.5, 0.5)
+    t = np.stack([np.arange(n), np.arange(n) + n, np.arange(n) + 2 * n], axis=1).astype(np.int32)
+    mesh = MeshData(v, t, synth.PALETTE[np.arange(n) % 8], v.min(axis=0), v.max(axis=0))
+    ns = 12
+    u = rng.uniform(4 * ns).reshape(ns, 4)
+    sph = SphereData(np.concatenate([(u[:, :3] - 0.5) * 0.8, 0.02 + 0.08 * u[:, 3:]], axis=1), synth.PALETTE[np.arange(ns) % 8])
+    u = rng.uniform(8)
+    p = scenario(resolution=72, shadows=True, shadow_samples=6, sub_pixel_res=1 + int(u[0] * 2.99), focal_blur=u[1] < 0.3,
+                 yaw_deg=360.0 * u[2], pitch_deg=80.0 * u[3] - 40.0, object_depth=0.9 + 1.2 * u[4], point_lighting=u[5] < 0.8,
+                 specular_lighting=u[6] < 0.5, subdivision=u[7] < 0.8)
+    got = lib.Scene(ctx, [mesh], sph).render(p, want_ids=True)
+    want = oracle.Scene([mesh], sph).render(p, want_ids=True, want_aux=True)
+    assert_parity(got, want, exact=True, what=f"soup seed {seed}")
+    assert got["stats"].hits_primary == want["stats"].hits_primary > 100
