@@ -284,8 +284,12 @@ __device__ __forceinline__ float cull_from(double limit, double t_off)
 // The thread's single stack is passed in (Counters::stack); returns the number of nodes visited.
 // ---------------------------------------------------------------------------------------------
 template <class BOX, class LEAF>
-__device__ __forceinline__ unsigned int walk_bvh(const BvhNode* __restrict__ nodes, int* __restrict__ stack, BOX box, LEAF leaf)
+__device__ __forceinline__ unsigned int walk_bvh(const BvhNode* __restrict__ nodes, int n_prims, int* __restrict__ stack, BOX box,
+                                                 LEAF leaf)
 {
+    // a handful of primitives (config 2's 12-triangle room): testing them all costs less than the ~10 box
+    // pairs of their tree.  Leaf order == storage order, so this is the whole array.
+    if (n_prims <= kTinyMesh) { leaf(0, n_prims); return 0; }
     int sp = 0;
     int cur = 0;
     unsigned int nv = 0;
@@ -329,7 +333,7 @@ __device__ __forceinline__ bool walk(const BvhNode* __restrict__ nodes, const vo
     bool found = false;
     float tcull = cull_from(ANY ? limit : best->rf, tr.t_off);
     const unsigned int nv = walk_bvh(
-        nodes, c->stack,
+        nodes, kTinyMesh + 1, c->stack,
         [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float* t) {
             return slab(tr, lox, loy, loz, hix, hiy, hiz, tcull, t);
         },
@@ -588,15 +592,15 @@ __device__ __forceinline__ int tri_filter(const TriFilt* __restrict__ t, const F
 // BVH walk with the filter at the leaves.  0 surely clear, 1 surely occluded, 2 cannot tell: then
 // unsure[0..*n_unsure) lists the triangles the exact arithmetic has to look at (every other triangle is
 // surely missed); *n_unsure > kMaxCand means too many to list.
-__device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, const FRay& r,
-                                               float V, int* unsure, int* n_unsure, Counters* c)
+__device__ __forceinline__ int walk_filter_any(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, int n_tris,
+                                               const FRay& r, float V, int* unsure, int* n_unsure, Counters* c)
 {
     bool hit = false;
     int nu = 0;
     int u0 = -1, u1 = -1, u2 = -1, u3 = -1;
     unsigned int nf = 0;
     c->node_visits += walk_bvh(
-        nodes, c->stack,
+        nodes, n_tris, c->stack,
         [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float* t) {
             return fslab(r, lox, loy, loz, hix, hiy, hiz, t);
         },
@@ -631,8 +635,8 @@ constexpr int kMaxCand = 4;
 // not exceed best_hi (everything else is surely missed or surely behind the best sure hit).
 struct FClosest { float best_hi; int best_k; int n_cand; int cand[kMaxCand]; float cand_lo[kMaxCand]; };
 
-__device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, FRay& r,
-                                                    float V, FClosest* out, XCounters* c)
+__device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, int n_tris,
+                                                    FRay& r, float V, FClosest* out, XCounters* c)
 {
     float best_hi = 1e30f;
     int best_k = -1;
@@ -641,7 +645,7 @@ __device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ 
     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
     unsigned int nf = 0;
     c->node_visits += walk_bvh(
-        nodes, c->stack,
+        nodes, n_tris, c->stack,
         [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float* t) {
             return fslab(r, lox, loy, loz, hix, hiy, hiz, t);
         },
@@ -734,7 +738,7 @@ __device__ __forceinline__ int spheres_filter(const DevScene& sc, d3 s, d3 dir, 
     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
     unsigned int nf = 0;
     *nv_out += walk_bvh(
-        sc.sphere_nodes, stack,
+        sc.sphere_nodes, sc.n_spheres, stack,
         [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float* t) {
             return fslab(r, lox, loy, loz, hix, hiy, hiz, t);
         },
@@ -872,7 +876,7 @@ __device__ __forceinline__ bool bundle_clear(const DevMesh& m, d3 end, d3 light,
     bool clear = true;
     unsigned int nf = 0;
     c->node_visits += walk_bvh(
-        m.nodes, c->stack,
+        m.nodes, m.n_tris, c->stack,
         [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float* t) {
             *t = 0.0f;                                      // (no front-to-back order needed: every leaf must pass)
             if (--budget < 0) clear = false;                // too much geometry near the cone: trace the rays
@@ -1002,7 +1006,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
             known = fray_setup_fwd(m, subdivision, s, dir, &r, &t0);
             if (known == 1) {
                 FClosest fc;
-                walk_filter_closest(m.nodes, m.filt, r, m.scale, &fc, c);
+                walk_filter_closest(m.nodes, m.filt, m.n_tris, r, m.scale, &fc, c);
                 sure_hit = fc.best_k >= 0;
                 if (fc.n_cand == 0) known = 0;
                 else if (fc.n_cand > kMaxCand) known = 2;
@@ -1202,7 +1206,7 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
                 FRay r;
                 int list[kMaxCand]; int n_list = 0;
                 int res = fray_setup(m, f.subdivision, anchor, dir, &r);
-                if (res == 1) res = walk_filter_any(m.nodes, m.filt, r, m.scale, list, &n_list, c);
+                if (res == 1) res = walk_filter_any(m.nodes, m.filt, m.n_tris, r, m.scale, list, &n_list, c);
                 if (n_list > kMaxCand) n_list = 0;                  // too many undecided triangles: full exact walk
                 if (f.filter_mode == 2) {
                     occ = occluded_mesh(m, f.subdivision, start, dir, nullptr, 0, xc);

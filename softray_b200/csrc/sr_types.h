@@ -72,6 +72,7 @@ constexpr int32_t kNoChild = -1;    // = a leaf of zero primitives; its box is t
 constexpr int kMaxLeafPrims = 15;        // fits the 4-bit count of a packed stack entry
 constexpr int kMaxBvhDepth  = 60;        // builder falls back to median splits to stay below this
 constexpr int kStackEntries = 64;
+constexpr int kTinyMesh = 16;            // filtered walks test this few primitives directly instead of walking their tree
 constexpr int kTlasStackEntries = 32;    // instance hierarchy (<= SOFTRAY_MAX_INSTANCES leaves)
 
 struct DevMesh {
