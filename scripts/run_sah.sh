@@ -1,3 +1,3 @@
-for c in 2.0 1.0 0.5 0.3; do echo "== isect $c"; SOFTRAY_SAH_ISECT=$c python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e | python -c "
+for c in 0.5 1.0 2.0 4.0; do echo "== isect $c"; for w in ${W:-config2}; do SOFTRAY_SAH_ISECT=$c python bench.py --workload $w --steps 5 --warmup 3 --no-cpu --no-e2e | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['config']['counters'])"; done
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['config']['workload'], round(d['ms_per_step'],3), d['config']['counters']['node_visits'], d['config']['counters']['filter_tests'])"; done; done

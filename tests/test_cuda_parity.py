@@ -419,3 +419,42 @@ def test_random_soups_and_spheres_against_oracle(lib, ctx, seed):
     want = oracle.Scene([mesh], sph).render(p, want_ids=True, want_aux=True)
     assert_parity(got, want, exact=True, what=f"soup seed {seed}")
     assert got["stats"].hits_primary == want["stats"].hits_primary > 100
+
+
+def test_config4_full_size_rows_against_oracle(lib, ctx):
+    """configs[3] as named (100 k-triangle mesh x 100 instances, 3840x2160, 16 spp): two full-width rows
+    against the oracle, which traces every instance for every ray."""
+    import oracle
+
+    meshes, _, p = synth.config4()
+    sc = lib.Scene(ctx, meshes)
+    orc = oracle.Scene(meshes)
+    for top in (700, 1403):
+        p.start_row, p.end_row = top, top
+        got = sc.render(p, want_ids=True)
+        want = orc.render(p, want_ids=True, want_aux=True)
+        sl = slice(top, top + 1)
+        sub = dict(pixels=got["pixels"][sl], ids=got["ids"][sl])
+        wsub = dict(pixels=want["pixels"][sl], ids=want["ids"][sl], cos_theta=want["cos_theta"][sl])
+        assert_parity(sub, wsub, what=f"config4 row {top}")
+        assert got["stats"].rays_primary == 3840 * 16 and got["stats"].hits_primary > 3840 * 8
+
+
+def test_config5_full_size_filter_modes_and_bands(lib, ctx):
+    """configs[4] as named (10 M triangles flattened, 7680x4320, 1 shadow ray per hit): a 96-row slice of
+    the 8K frame rendered with the FP32 filters, with the FP64 reference arithmetic only, and as two
+    interleaved bands (the multi-GPU partition) gives the same pixels and ids."""
+    meshes, _, p = synth.config5()
+    sc = lib.Scene(ctx, meshes)
+    p.start_row, p.end_row = 2100, 2195
+    a = sc.render(p, want_ids=True)
+    p.filter_mode = abi.FILTER_OFF
+    b = sc.render(p, want_ids=True)
+    assert np.array_equal(a["pixels"], b["pixels"]) and np.array_equal(a["ids"], b["ids"])
+    assert a["stats"].hits_primary == b["stats"].hits_primary > 100_000 and a["stats"].rays_shadow == a["stats"].hits_primary
+    p.filter_mode = abi.FILTER_AUTO
+    px = np.zeros_like(a["pixels"])
+    for r in range(2):
+        p.band_height, p.band_count, p.band_index = 8, 2, r
+        sc.render(p, pixels=px)
+    assert np.array_equal(px[2100:2196], a["pixels"][2100:2196])
