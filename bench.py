@@ -87,7 +87,7 @@ def algorithmic_work(st, frame):
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU during the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, index, period=0.002):
+    def __init__(self, index, period=0.0005):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -132,7 +132,7 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "window": "warm-up + timed steps"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -283,11 +283,13 @@ def main():
         counters = dict(zip(sorted(counters), [int(v) for v in t.tolist()]))
     rays = counters["rays_primary"] + counters["rays_shadow"] + counters["rays_secondary"]
 
+    # clocks are sampled from the first warm-up step to the end of the timed region: a config-2 frame takes
+    # under a millisecond, so the timed region alone is shorter than a few NVML polls
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
     for a, b in ev:

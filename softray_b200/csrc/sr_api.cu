@@ -812,6 +812,7 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     p->smem = sizeof(DevInstance) * (size_t)f.n_instances + sizeof(double) * 3 * (size_t)f.shadow_samples;
     int occ = render_kernel_occupancy((int)p->smem);
     if (occ < 1) occ = 1;
+    { const int cap = env_int("SOFTRAY_BLOCKS_PER_SM", 0); if (cap > 0 && cap < occ) occ = cap; }   // experiments
     const long long n_tiles = (long long)f.tiles_x * f.tiles_y;
     long long grid = (long long)ctx->sm_count * occ;
     const long long need = (n_tiles + 3) / 4;            // 4 warps per block
