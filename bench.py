@@ -242,7 +242,8 @@ def main():
     meshes, spheres, frame, desc = workload(args.workload, args.scale)
     W, H = frame.width, frame.height
     t0 = time.perf_counter()
-    scene = lib.Scene(ctx, meshes, spheres)
+    accel = {"bvh": abi.ACCEL_BVH, "lbvh": abi.ACCEL_LBVH}[os.environ.get("SOFTRAY_ACCEL", "bvh")]   # experiment knob
+    scene = lib.Scene(ctx, meshes, spheres, accel=accel)
     scene_ms = (time.perf_counter() - t0) * 1e3
 
     bh = args.band_height or multi_gpu.default_band_height(H, world)
@@ -412,7 +413,7 @@ def main():
                        "rays_per_step": rays, "counters": counters, "l2": "flushed between timed steps (256 MB fill)",
                        "partition": (f"{world} ranks, interleaved bands of {bh} rows, gather={args.gather}" if world > 1
                                      else "single GPU"),
-                       "scene_create_ms": scene_ms, "wall_ms_timed_region": wall_ms},
+                       "scene_create_ms": scene_ms, "accel": os.environ.get("SOFTRAY_ACCEL", "bvh"), "wall_ms_timed_region": wall_ms},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * world,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
         }

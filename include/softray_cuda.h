@@ -91,6 +91,10 @@ typedef struct softray_sphere {
 #define SOFTRAY_ACCEL_BVH    0   /* library-built BVHs (default); results identical to brute force  */
 #define SOFTRAY_ACCEL_BRUTE  1   /* linear scan of every primitive per ray, like
                                     GeometryCollection.IntersectRay (GeometryCollection.cs:44-69)   */
+#define SOFTRAY_ACCEL_LBVH   2   /* meshes flattened and their trees built ON THE DEVICE (Morton-code
+                                    LBVH, deterministic): scene_create in milliseconds for dynamic
+                                    scenes; slower to trace than the host-built SAH tree.  Spheres
+                                    still use the host builder.  Results identical.                 */
 
 typedef struct softray_scene_desc {
     const softray_mesh*   meshes;     int32_t n_meshes;   int32_t accel;  /* SOFTRAY_ACCEL_*       */

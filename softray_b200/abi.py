@@ -18,6 +18,7 @@ E_FORMAT = -7
 
 ACCEL_BVH = 0
 ACCEL_BRUTE = 1
+ACCEL_LBVH = 2
 
 FILTER_AUTO = 0
 FILTER_OFF = 1

@@ -31,6 +31,9 @@ cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstan
                           int grid_blocks, cudaStream_t stream);
 int render_kernel_occupancy(int smem_bytes);
 cudaError_t measure_fma_peak(bool fp64, int sm_count, cudaStream_t stream, double* tflops);
+cudaError_t build_mesh_on_device(const double* h_verts, int32_t n_verts, const int32_t* h_vidx, const uint32_t* h_argb, int32_t n_tris,
+                                 const double bmin[3], const double bmax[3], float pad, int leaf_max, cudaStream_t stream, TriRec** out_tris,
+                                 TriFilt** out_filt, BvhNode** out_nodes, int32_t* out_n_nodes, int32_t* out_depth, int* status);
 cudaError_t launch_resolve(const uint32_t* d_src, uint32_t* d_dst, int dst_w, int dst_h, int aa, int style, uint32_t background,
                            cudaStream_t stream);
 }  // namespace sr
@@ -78,6 +81,9 @@ struct softray_scene {
     uint64_t fingerprint = 1469598103934665603ull;
     size_t device_bytes = 0;
     double all_min[3] = {1e300, 1e300, 1e300}, all_max[3] = {-1e300, -1e300, -1e300};   // every primitive
+    // buffers built on the device (SOFTRAY_ACCEL_LBVH): folded into the fingerprint on first request
+    struct DevBuf { const void* ptr; size_t bytes; };
+    std::vector<DevBuf> unhashed;
 };
 
 static thread_local std::string g_last_error;
@@ -356,6 +362,12 @@ inline int env_int(const char* name, int dflt)
     return (e && *e) ? std::atoi(e) : dflt;
 }
 
+// primitives per leaf of the device-built tree (a radix-tree subtree this small becomes one leaf);
+// SOFTRAY_LBVH_LEAF overrides it for experiments.  Measured on one B200 (config3 / config5 ms per frame):
+// 1: 65.7 / 20.9, 2: 67.2 / 21.2, 4: 74.5 / 22.9, 8: 90.3 / 26.6 (host SAH tree: 48.7 / 17.1)
+constexpr int kLbvhLeaf = 1;
+inline int lbvh_leaf_max() { const int v = env_int("SOFTRAY_LBVH_LEAF", kLbvhLeaf); return v < 1 ? 1 : (v > kMaxLeafPrims ? kMaxLeafPrims : v); }
+
 inline float traversal_pad(double max_coord) { return round_up(std::ldexp(std::fmax(max_coord, 1e-30), -18)); }
 
 }  // namespace
@@ -459,11 +471,47 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
 {
     softray_ctx* ctx = sc->ctx;
     const bool brute = desc->accel == SOFTRAY_ACCEL_BRUTE;
+    const bool lbvh = desc->accel == SOFTRAY_ACCEL_LBVH;
     std::vector<DevMesh> meshes((size_t)desc->n_meshes);
     for (int32_t mi = 0; mi < desc->n_meshes; mi++) {
         const softray_mesh& m = desc->meshes[mi];
         if (m.n_tris < 0 || m.n_verts < 0 || (m.n_tris > 0 && (!m.verts_xyz || !m.tri_vidx || !m.tri_argb)))
             return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: mesh arrays missing");
+        if (lbvh) {
+            // flatten + tree on the device (sr_lbvh.cu); same records, its own tree
+            DevMesh& dm = meshes[(size_t)mi];
+            std::memset(&dm, 0, sizeof dm);
+            dm.n_tris = m.n_tris;
+            for (int k = 0; k < 3; k++) {
+                dm.bmin[k] = m.bbox_min[k]; dm.bmax[k] = m.bbox_max[k];
+                dm.fmin[k] = (float)m.bbox_min[k]; dm.fmax[k] = (float)m.bbox_max[k];
+                sc->all_min[k] = std::fmin(sc->all_min[k], m.bbox_min[k]); sc->all_max[k] = std::fmax(sc->all_max[k], m.bbox_max[k]);
+            }
+            dm.scale = round_up(max_abs3(m.bbox_min, m.bbox_max));
+            sc->mesh_tris.push_back(m.n_tris);
+            { softray_scene::V3 a, b; for (int k = 0; k < 3; k++) { a.v[k] = m.bbox_min[k]; b.v[k] = m.bbox_max[k]; }
+              sc->mesh_bmin.push_back(a); sc->mesh_bmax.push_back(b); }
+            if (m.n_tris == 0) continue;
+            TriRec* d_tris = nullptr; TriFilt* d_filt = nullptr; BvhNode* d_nodes = nullptr;
+            int32_t n_nodes = 0, depth = 0; int status = 0;
+            const auto t_build = std::chrono::steady_clock::now();
+            SR_CUDA(ctx, build_mesh_on_device(m.verts_xyz, m.n_verts, m.tri_vidx, m.tri_argb, m.n_tris, m.bbox_min, m.bbox_max,
+                                              traversal_pad(max_abs3(m.bbox_min, m.bbox_max)), lbvh_leaf_max(), ctx->stream, &d_tris, &d_filt, &d_nodes,
+                                              &n_nodes, &depth, &status));
+            if (env_int("SOFTRAY_BUILD_TIMING", 0))
+                std::fprintf(stderr, "softray: mesh %d (%d triangles) flattened + tree built on the device in %.2f ms\n", mi, m.n_tris,
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build).count());
+            if (status == 1) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: vertex index out of range");
+            if (status == 2) return fail(ctx, SOFTRAY_E_VERTEX_OUTSIDE_BBOX, "A triangle vertex is outside the bounding box");
+            if (status == 3) return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_scene_create: device-built tree too deep (use SOFTRAY_ACCEL_BVH)");
+            sc->allocs.push_back(d_tris); sc->allocs.push_back(d_filt); sc->allocs.push_back(d_nodes);
+            const size_t b_tris = sizeof(TriRec) * (size_t)m.n_tris, b_filt = sizeof(TriFilt) * (size_t)m.n_tris,
+                         b_nodes = sizeof(BvhNode) * (size_t)n_nodes;
+            sc->device_bytes += b_tris + b_filt + b_nodes;
+            sc->unhashed.push_back({d_tris, b_tris}); sc->unhashed.push_back({d_nodes, b_nodes}); sc->unhashed.push_back({d_filt, b_filt});
+            dm.tris = d_tris; dm.filt = d_filt; dm.nodes = d_nodes; dm.n_nodes = n_nodes;
+            continue;
+        }
         std::vector<TriRec> recs((size_t)m.n_tris);
         std::vector<PrimBounds> bounds((size_t)m.n_tris);
         std::atomic<int> bad(0);            // 1: vertex index out of range, 2: vertex outside the bounding box
@@ -606,7 +654,7 @@ extern "C" int softray_scene_create(softray_ctx* ctx, const softray_scene_desc* 
     if (desc->n_meshes < 0 || desc->n_spheres < 0 || (desc->n_meshes > 0 && !desc->meshes) ||
         (desc->n_spheres > 0 && !desc->spheres))
         return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: bad counts or NULL arrays");
-    if (desc->accel != SOFTRAY_ACCEL_BVH && desc->accel != SOFTRAY_ACCEL_BRUTE)
+    if (desc->accel != SOFTRAY_ACCEL_BVH && desc->accel != SOFTRAY_ACCEL_BRUTE && desc->accel != SOFTRAY_ACCEL_LBVH)
         return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: unknown accel");
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     softray_scene* sc = new (std::nothrow) softray_scene();
@@ -629,6 +677,17 @@ extern "C" int softray_scene_create(softray_ctx* ctx, const softray_scene_desc* 
 extern "C" int softray_scene_fingerprint(const softray_scene* scene, uint64_t* out)
 {
     if (!scene || !out) return fail(nullptr, SOFTRAY_E_INVALID_ARG, "softray_scene_fingerprint: NULL argument");
+    softray_scene* sc = const_cast<softray_scene*>(scene);
+    if (!sc->unhashed.empty()) {           // device-built buffers: read them back once
+        SR_CUDA(sc->ctx, cudaSetDevice(sc->ctx->device));
+        std::vector<unsigned char> host;
+        for (const softray_scene::DevBuf& b : sc->unhashed) {
+            host.resize(b.bytes);
+            SR_CUDA(sc->ctx, cudaMemcpy(host.data(), b.ptr, b.bytes, cudaMemcpyDeviceToHost));
+            fnv(&sc->fingerprint, host.data(), b.bytes);
+        }
+        sc->unhashed.clear();
+    }
     *out = scene->fingerprint;
     return SOFTRAY_OK;
 }
@@ -728,7 +787,7 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     f.band_count = banded ? fr->band_count : 1;
     f.band_index = banded ? fr->band_index : 0;
     // the FP32 filter needs the BVH layout (filter records live in leaf order)
-    f.filter_mode = scene->dev.accel == SOFTRAY_ACCEL_BVH ? fr->filter_mode : SOFTRAY_FILTER_OFF;
+    f.filter_mode = scene->dev.accel != SOFTRAY_ACCEL_BRUTE ? fr->filter_mode : SOFTRAY_FILTER_OFF;
 
     if (f.shadows && (ctx->cached_samples != f.shadow_samples || ctx->cached_seed != fr->random_seed)) {
         area_light_offsets(fr->random_seed, f.shadow_samples, ctx->h_offsets);
@@ -773,7 +832,7 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     // composite frame: BVH over the view-space boxes of the instances (the reference traces
     // instances one after the other over the whole frame, Renderer.cs:746-755)
     f.tlas_nodes = nullptr; f.tlas_order = nullptr; ctx->tlas_nodes_used = 0;
-    if (fr->n_instances > 1 && scene->dev.accel == SOFTRAY_ACCEL_BVH) {
+    if (fr->n_instances > 1 && scene->dev.accel != SOFTRAY_ACCEL_BRUTE) {
         std::vector<PrimBounds> boxes((size_t)fr->n_instances);
         double big = 0.0;
         for (int32_t i = 0; i < fr->n_instances; i++) {
