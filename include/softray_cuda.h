@@ -57,7 +57,9 @@ typedef struct softray_scene softray_scene;  /* opaque: device-resident SoA geom
  * the reference (it has no device); lifetime = where Renderer caches geometry_simple /
  * geometry_subdivided / rootGeometry (Renderer.cs:173-175) and Renderer.Dispose (:236-255). */
 int  softray_create(int32_t device_ordinal, softray_ctx** out);
-void softray_destroy(softray_ctx* ctx);
+void softray_destroy(softray_ctx* ctx);   /* also releases the scenes the context still owns; a handle that
+                                            is not live (NULL, already destroyed) is ignored -- finalisers may
+                                            run in any order (Renderer.Dispose vs the .NET finaliser thread) */
 const char* softray_last_error(const softray_ctx* ctx);
 int  softray_abi_version(void);
 /* sizeof of the PODs below as this library was compiled: 0 mesh, 1 sphere, 2 scene_desc,
@@ -108,7 +110,7 @@ typedef struct softray_scene_desc {
  * including its vertex-inside-bbox check).  Deterministic: the same input gives a bit-identical
  * device layout on every call. */
 int  softray_scene_create(softray_ctx* ctx, const softray_scene_desc* desc, softray_scene** out);
-void softray_scene_destroy(softray_scene* scene);
+void softray_scene_destroy(softray_scene* scene);   /* no-op on a scene already released (twice, or with its context) */
 
 /* Layout fingerprint (FNV-1a over every device-resident scene buffer, in upload order) --
  * the "bit-identical layout across runs" check. */

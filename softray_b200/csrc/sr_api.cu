@@ -18,7 +18,9 @@
 #include <algorithm>
 #include <atomic>
 #include <string>
+#include <mutex>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/softray_cuda.h"
@@ -63,6 +65,7 @@ struct softray_ctx {
     int32_t tlas_nodes_used = 0;
     double* h_offsets = nullptr;
     DevCounters* h_counters = nullptr;
+    std::vector<struct softray_scene*> scenes;   // scenes created in this context and not yet destroyed
     // device framebuffer of the host-buffer entry point (grown on demand)
     uint32_t* d_pixels = nullptr;
     int32_t* d_ids = nullptr;
@@ -87,6 +90,12 @@ struct softray_scene {
 };
 
 static thread_local std::string g_last_error;
+
+// Live handles.  A host runtime with non-deterministic finalisation (the .NET finaliser thread, CPython at
+// interpreter exit) may release a context before its scenes, or a scene twice: softray_destroy therefore
+// releases the scenes its context still owns, and destroying a handle that is no longer live is a no-op.
+static std::mutex g_live_mutex;
+static std::unordered_set<const void*> g_live_ctx, g_live_scenes;
 
 static int fail(softray_ctx* ctx, int code, const std::string& msg)
 {
@@ -395,9 +404,19 @@ extern "C" const char* softray_last_error(const softray_ctx* ctx)
     return ctx ? ctx->err.c_str() : g_last_error.c_str();
 }
 
+static void release_scene(softray_scene* scene);
+
 extern "C" void softray_destroy(softray_ctx* ctx)
 {
     if (!ctx) return;
+    std::vector<softray_scene*> orphans;
+    {
+        std::lock_guard<std::mutex> lock(g_live_mutex);
+        if (!g_live_ctx.erase(ctx)) return;             // not (or no longer) a live context
+        orphans.swap(ctx->scenes);
+        for (softray_scene* sc : orphans) g_live_scenes.erase(sc);
+    }
+    for (softray_scene* sc : orphans) release_scene(sc);
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_insts); cudaFree(ctx->d_offsets); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_counters);
@@ -444,6 +463,7 @@ extern "C" int softray_create(int32_t device_ordinal, softray_ctx** out)
         SR_CUDA(ctx, cudaMallocHost((void**)&ctx->h_counters, sizeof(DevCounters)));
         return SOFTRAY_OK;
     }();
+    { std::lock_guard<std::mutex> lock(g_live_mutex); g_live_ctx.insert(ctx); }
     if (rc != SOFTRAY_OK) {
         g_last_error = ctx->err;
         softray_destroy(ctx);
@@ -459,6 +479,17 @@ extern "C" int softray_create(int32_t device_ordinal, softray_ctx** out)
 extern "C" void softray_scene_destroy(softray_scene* scene)
 {
     if (!scene) return;
+    {
+        std::lock_guard<std::mutex> lock(g_live_mutex);
+        if (!g_live_scenes.erase(scene)) return;        // already released (with its context, or twice)
+        std::vector<softray_scene*>& v = scene->ctx->scenes;
+        v.erase(std::remove(v.begin(), v.end(), scene), v.end());
+    }
+    release_scene(scene);
+}
+
+static void release_scene(softray_scene* scene)
+{
     if (scene->ctx) {
         cudaSetDevice(scene->ctx->device);
         cudaStreamSynchronize(scene->ctx->stream);
@@ -667,9 +698,10 @@ extern "C" int softray_scene_create(softray_ctx* ctx, const softray_scene_desc* 
         rc = fail(ctx, SOFTRAY_E_OOM, "softray_scene_create: out of host memory");
     }
     if (rc != SOFTRAY_OK) {
-        softray_scene_destroy(sc);
+        release_scene(sc);
         return rc;
     }
+    { std::lock_guard<std::mutex> lock(g_live_mutex); g_live_scenes.insert(sc); ctx->scenes.push_back(sc); }
     *out = sc;
     return SOFTRAY_OK;
 }

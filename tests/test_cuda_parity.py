@@ -458,3 +458,28 @@ def test_config5_full_size_filter_modes_and_bands(lib, ctx):
         p.band_height, p.band_count, p.band_index = 8, 2, r
         sc.render(p, pixels=px)
     assert np.array_equal(px[2100:2196], a["pixels"][2100:2196])
+
+
+def test_handles_may_be_released_in_any_order(lib, obj_mesh):
+    """Finalisers run in any order (Renderer.Dispose vs the finaliser thread, CPython at exit): a context
+    releases the scenes it still owns, and destroying a dead handle is a no-op (include/softray_cuda.h)."""
+    import ctypes as C
+
+    L = lib.load()
+    c = lib.Context(0)
+    s1 = lib.Scene(c, [obj_mesh])
+    s2 = lib.Scene(c, [obj_mesh], accel=abi.ACCEL_LBVH)
+    h_ctx, h1, h2 = C.c_void_p(c._h.value), C.c_void_p(s1._h.value), C.c_void_p(s2._h.value)
+    s1.render(scenario(resolution=16))
+    L.softray_scene_destroy(h1)
+    L.softray_scene_destroy(h1)          # twice
+    L.softray_destroy(h_ctx)             # takes s2 with it
+    L.softray_scene_destroy(h2)          # after its context
+    L.softray_destroy(h_ctx)             # twice
+    for o in (s1, s2, c):
+        o._h = C.c_void_p()
+    # and the library still works
+    c2 = lib.Context(0)
+    out = lib.Scene(c2, [obj_mesh]).render(scenario(resolution=16))
+    assert (out["pixels"] >> 24 == 0xFF).all()
+    c2.close()
