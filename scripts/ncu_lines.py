@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""Per-source-line / per-function profile of one kernel from an .ncu-rep (--set full, -lineinfo build).
+Joins the SASS page of the report (instructions executed + stall samples per address) with nvdisasm's
+line table of the same cubin.  usage: ncu_lines.py <report.ncu-rep> <cubin> <source.cu> [top]"""
+import csv
+import re
+import subprocess
+import sys
+from collections import defaultdict
+
+rep, cubin, src = sys.argv[1:4]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+HELPER_END = 70   # source lines below this are one-line arithmetic helpers
+
+# --- line table: kernel text offset -> source line ------------------------------------------------
+dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
+sections = {}   # section name -> {offset: line}
+cur, line = None, 0
+for l in dis.splitlines():
+    m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
+    if m:
+        cur = sections.setdefault(m.group(1), {}); line = 0; continue
+    m = re.match(r'\s*//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', l)
+    if m:
+        mine = src.split("/")[-1]
+        line = int(m.group(2)) if m.group(1).endswith(mine) else -1
+        # one-line helpers (the FP64 wrappers at the top of the file) and toolkit headers: charge the call site
+        if (line < HELPER_END) and m.group(3) and m.group(3).endswith(mine):
+            line = int(m.group(4))
+        continue
+    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
+    if m and cur is not None:
+        cur[int(m.group(1), 16)] = (line, m.group(2).strip())
+
+# --- function extents of the source (column-0 definitions) ------------------------------------------
+text = open(src).read().splitlines()
+func_of = [None] * (len(text) + 2)
+name, depth_start = None, None
+for i, l in enumerate(text, 1):
+    if name is None:
+        m = re.match(r"^(?:template.*>\s*)?(?:static\s+)?(?:__device__|__global__|__host__|inline|__forceinline__|__noinline__|[\w:<>\*&]+\s)+.*?(\w+)\s*\(", l)
+        if m and not l.startswith((" ", "\t", "//", "#", "}")) and not l.rstrip().endswith(";"):
+            name = m.group(1)
+    if name is not None:
+        func_of[i] = name
+        if l.startswith("}"):
+            name = None
+
+# --- report rows ------------------------------------------------------------------------------------
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
+kname = re.search(r'"Kernel Name","([^"(]+)', raw[0]).group(1)
+rows = list(csv.reader(raw[1:]))
+hdr = rows[0]
+ia, ii, isamp, ithr = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
+stall_cols = [(k, h) for k, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+body = rows[1:]
+base = int(body[0][ia], 16)
+sec = next((v for k, v in sections.items() if "render_kernel" in k and kname.split("::")[-1] in k), None) or max(sections.values(), key=len)
+
+by_line = defaultdict(lambda: [0, 0, 0])
+by_func = defaultdict(lambda: [0, 0, 0, defaultdict(int)])
+tot_i = tot_s = 0
+for r in body:
+    off = int(r[ia], 16) - base
+    ln = sec.get(off, (0, ""))[0]
+    n, s, t = int(r[ii] or 0), int(r[isamp] or 0), int(r[ithr] or 0)
+    tot_i += n; tot_s += s
+    by_line[ln][0] += n; by_line[ln][1] += s; by_line[ln][2] += t
+    f = func_of[ln] if 0 < ln < len(func_of) and func_of[ln] else f"<line {ln}>"
+    by_func[f][0] += n; by_func[f][1] += s; by_func[f][2] += t
+    for k, h in stall_cols:
+        v = int(r[k] or 0)
+        if v:
+            by_func[f][3][h] += v
+
+print(f"kernel {kname}: {tot_i} warp instructions, {tot_s} samples, {len(body)} SASS instructions")
+print("\nby function (innermost inlined frame):  inst%  samples%  lanes  top stalls")
+for f, (n, s, t, st) in sorted(by_func.items(), key=lambda kv: -kv[1][1])[:top]:
+    tops = ", ".join(f"{h[6:]} {100.0 * v / max(s, 1):.0f}%" for h, v in sorted(st.items(), key=lambda kv: -kv[1])[:4])
+    print(f"  {f:34s} {100.0 * n / tot_i:6.2f} {100.0 * s / tot_s:7.2f}  {t / max(n, 1):5.1f}  {tops}")
+print("\nby line:  line  inst%  samples%  source")
+for ln, (n, s, t) in sorted(by_line.items(), key=lambda kv: -kv[1][1])[:top]:
+    code = text[ln - 1].strip()[:110] if 0 < ln <= len(text) else ""
+    print(f"  {ln:5d} {100.0 * n / tot_i:6.2f} {100.0 * s / tot_s:7.2f}  {code}")
