@@ -364,6 +364,7 @@ inline double sah_isect_cost(double dflt)
     return dflt;
 }
 
+constexpr long long kPhaseSyncMaxPrims = 65536;
 constexpr int kBundleMinSamples = 16, kBundleBudget = 384;   // budget counts child boxes: 384 = 192 nodes
 inline int env_int(const char* name, int dflt)
 {
@@ -834,6 +835,18 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
         f.light_radius = round_up(std::sqrt(r2) * (1.0 + 1e-6));
         // a cone walk pays off when it replaces many rays and stays cheap: bounded to a few single-ray walks
         f.bundle_budget = f.shadow_samples >= kBundleMinSamples ? env_int("SOFTRAY_BUNDLE_BUDGET", kBundleBudget) : 0;
+    }
+
+    // Stage barriers (sr_render.cu "Phase synchronisation") need every thread of a block in every stage: single-
+    // instance frames only (a composite frame calls the per-instance search from inside its hierarchy walk).  They pay
+    // where instruction fetch, not the walks, bounds the camera rays: a small cache-resident scene (short walks of
+    // similar length) under a frame with enough tiles to keep every warp busy.  SOFTRAY_PHASE_SYNC=0/1 overrides.
+    {
+        long long prims = scene->dev.n_spheres;
+        for (int32_t t : scene->mesh_tris) prims += t;
+        const long long tiles = (long long)((f.width + 7) / 8) * ((rows + 3) / 4) / (f.band_count > 0 ? f.band_count : 1);
+        const bool small_scene = prims <= kPhaseSyncMaxPrims && tiles >= 8LL * ctx->sm_count * (768 / 32);
+        f.phase_sync = fr->n_instances == 1 ? (env_int("SOFTRAY_PHASE_SYNC", small_scene ? 1 : 0) != 0) : 0;
     }
 
     int32_t base = 0;

@@ -20,6 +20,20 @@ namespace sr {
 // ---------------------------------------------------------------------------------------------
 // exact FP64 vector helpers (no contraction, left-to-right like Engine3D/Vector.cs)
 // ---------------------------------------------------------------------------------------------
+// Phase synchronisation (profiles/r01s_instruction_fetch_findings.md).  The SM's instruction cache holds ~2 K
+// instructions and the camera-ray path is several times that, so a frame whose time goes into camera rays is bound
+// by instruction fetch.  While `sync` is on, the warps of a block fetch their tiles together and meet at barriers
+// between the stages of a camera ray (sphere search | exact spheres | mesh search | root-box clip + exact triangles |
+// shading), so they run the same few hundred instructions at about the same time and share the fetched lines.
+// Measured on one B200 (ms per frame, free-running -> synchronised, 256-thread blocks): config2 0.767 -> 0.700;
+// but config3 48.3 -> 51.4 and config5 17.1 -> 19.2 (long walks of very different lengths: the warps wait at the
+// barriers longer than the shared fetches save), so the host turns it on for small scenes only (sr_api.cu).
+// The flag is uniform over the launch; every thread of a block reaches every SR_SYNC_POINT while it is on.
+#ifndef SR_THREADS
+#define SR_THREADS 256
+#endif
+#define SR_SYNC_POINT(on) do { if (on) __syncthreads(); } while (0)
+
 struct d3 { double x, y, z; };
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -204,6 +218,59 @@ __device__ __forceinline__ bool reference_clip(const double* mn, const double* m
     if (start_inside) return true;
     *start = p;
     *offset = ddiv(vlen(vsub(s, p)), vlen(dir));   // originalStart.Distance(start) / dir.Length
+    return true;
+}
+
+// reference_clip when the answer is obvious: the start lies outside the box and the ray enters through the
+// interior of ONE face.  ClipLineSegment's loop (AxisAlignedBox.cs:175-216) then keeps exactly that face's crossing:
+// of the other five candidates, the far faces lie further along the segment and the other near faces are crossed
+// where the ray is still outside the box on the entry axis -- all by `margin` in space, >> the 1e-10 of
+// ContainsPoint (AxisAlignedBox.cs:143-149) and >> the error of the FP32 estimate that decides this (~1e-6 of the
+// operands).  The crossing itself is computed with the reference's operations for that one plane, so *start and
+// *offset are bit-identical to reference_clip's (1 FP64 division instead of 7, no 6 x ContainsPoint).  false: not
+// that clear -- run reference_clip.  (SR_CLIP_CHECK builds run both and count differences as filter mismatches.)
+__device__ __forceinline__ bool reference_clip_face(const double* mn, const double* mx, d3* start, d3 dir, double* offset)
+{
+    const d3 s = *start;
+    const float sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
+    const float gx = (float)dir.x * 10000.0f, gy = (float)dir.y * 10000.0f, gz = (float)dir.z * 10000.0f;   // the segment's span
+    const float agx = fabsf(gx), agy = fabsf(gy), agz = fabsf(gz);
+    if (!(fminf(agx, fminf(agy, agz)) > 1e-20f) || !(fmaxf(agx, fmaxf(agy, agz)) < 1e30f)) return false;
+    const float lox = (float)mn[0], loy = (float)mn[1], loz = (float)mn[2], hix = (float)mx[0], hiy = (float)mx[1], hiz = (float)mx[2];
+    const float ix = 1.0f / gx, iy = 1.0f / gy, iz = 1.0f / gz;
+    const float ax = (lox - sx) * ix, bx = (hix - sx) * ix, ay = (loy - sy) * iy, by = (hiy - sy) * iy,
+                az = (loz - sz) * iz, bz = (hiz - sz) * iz;
+    const float nx = fminf(ax, bx), fx = fmaxf(ax, bx), ny = fminf(ay, by), fy = fmaxf(ay, by), nz = fminf(az, bz), fz = fmaxf(az, bz);
+    const float t_in = fmaxf(nx, fmaxf(ny, nz));
+    const float big = fmaxf(fmaxf(fabsf(sx), fabsf(sy)), fmaxf(fabsf(sz), fmaxf(fmaxf(fabsf(lox), fabsf(hix)),
+                            fmaxf(fmaxf(fabsf(loy), fabsf(hiy)), fmaxf(fabsf(loz), fabsf(hiz))))));
+    const float margin = 1e-4f * big;
+    if (!(t_in < 0.999f)) return false;
+    int axis;                  // entry axis; its near plane is the min plane when the span is positive
+    float ga;
+    if (t_in == nx) { axis = 0; ga = agx; } else if (t_in == ny) { axis = 1; ga = agy; } else { axis = 2; ga = agz; }
+    // the start is outside by `margin` on the entry axis, the box is not flat there
+    if (!(t_in * ga > margin)) return false;
+    if (!(((axis == 0 ? fx : axis == 1 ? fy : fz) - t_in) * ga > margin)) return false;
+    // on the other two axes: the entry point lies inside the slab by `margin`, and the slab's near plane is crossed
+    // while the ray is still `margin` outside the box on the entry axis
+    if (axis != 0 && (!((t_in - nx) * agx > margin) || !((fx - t_in) * agx > margin) || !((t_in - nx) * ga > margin))) return false;
+    if (axis != 1 && (!((t_in - ny) * agy > margin) || !((fy - t_in) * agy > margin) || !((t_in - ny) * ga > margin))) return false;
+    if (axis != 2 && (!((t_in - nz) * agz > margin) || !((fz - t_in) * agz > margin) || !((t_in - nz) * ga > margin))) return false;
+    // the reference's arithmetic for that plane (box_first_crossing, k = axis or axis + 3)
+    const d3 end = vadd(s, vscale(dir, 10000.0));
+    const d3 span = vsub(end, s);
+    const double sa = axis == 0 ? s.x : axis == 1 ? s.y : s.z;
+    const double ea = axis == 0 ? end.x : axis == 1 ? end.y : end.z;
+    const double da = axis == 0 ? dir.x : axis == 1 ? dir.y : dir.z;
+    const bool min_plane = da > 0.0;
+    const double num = min_plane ? dsub(sa, mn[axis]) : dsub(mx[axis], sa);
+    const double den = min_plane ? dsub(sa, ea) : dsub(ea, sa);
+    const double lf = ddiv(num, den);
+    if (!(0.0 <= lf && lf <= 1.0)) return false;              // (cannot happen inside the margins; stay safe)
+    const d3 p = vadd(s, vscale(span, lf));
+    *start = p;
+    *offset = ddiv(vlen(vsub(s, p)), vlen(dir));               // originalStart.Distance(start) / dir.Length
     return true;
 }
 
@@ -937,7 +1004,18 @@ __device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivisio
 {
     d3 ts = s; double offset = 0.0;
     *ts_out = s; *offset_out = 0.0;
-    if (subdivision && !reference_clip(m.bmin, m.bmax, &ts, dir, &offset)) return;
+    if (subdivision) {
+        // (a candidate list means the filter is on: SOFTRAY_FILTER_OFF / _VERIFY always take reference_clip)
+        bool clipped = n_list > 0 && reference_clip_face(m.bmin, m.bmax, &ts, dir, &offset);
+#ifdef SR_CLIP_CHECK
+        if (clipped) {
+            d3 ts2 = s; double offset2 = 0.0;
+            const bool ok2 = reference_clip(m.bmin, m.bmax, &ts2, dir, &offset2);
+            if (!ok2 || ts2.x != ts.x || ts2.y != ts.y || ts2.z != ts.z || offset2 != offset) c->filter_mismatch++;
+        }
+#endif
+        if (!clipped && !reference_clip(m.bmin, m.bmax, &ts, dir, &offset)) return;
+    }
     *ts_out = ts; *offset_out = offset;
     if (n_list > 0) {
         for (int j = 0; j < n_list; j++) {
@@ -964,7 +1042,7 @@ __device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivisio
 
 // IRayIntersectable.IntersectRay of rootGeometry for a camera / reflection ray: the nearest hit.
 __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, int filter_mode, d3 s, d3 dir,
-                                            Hit* h, XCounters* c)
+                                            Hit* h, XCounters* c, bool sync)
 {
     // --- spheres (tested first in list order) ---
     BestPrim bs; bs.rf = kNoHit; bs.k = -1; bs.index = 0x7fffffff;
@@ -978,6 +1056,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
             known = spheres_filter<false>(sc, s, dir, list, &n_list, &nv, &nf, c->stack);
             c->node_visits += nv; c->filter_tests += nf;
         }
+        SR_SYNC_POINT(sync);
         const bool listed = known == 2 && n_list >= 1 && n_list <= kMaxCand;
         if (filter_mode == 2) {
             spheres_closest_exact(sc, s, dirn, nullptr, 0, &bs, c);
@@ -993,6 +1072,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
             spheres_closest_exact(sc, s, dirn, nullptr, 0, &bs, c);
         }
     }
+    SR_SYNC_POINT(sync);
     // --- mesh ---
     BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
     d3 ts = s; double offset = 0.0;
@@ -1016,6 +1096,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
                 }
             }
         }
+        SR_SYNC_POINT(sync);
         if (filter_mode == 2) {
             mesh_closest_exact(m, subdivision, s, dir, nullptr, 0, &bt, &ts, &offset, c);
             bool in_list = bt.k < 0;
@@ -1033,6 +1114,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
             mesh_closest_exact(m, subdivision, s, dir, nullptr, 0, &bt, &ts, &offset, c);
         }
     }
+    SR_SYNC_POINT(sync);
     const double rf_tri = bt.k >= 0 ? dadd(bt.rf, offset) : kNoHit;   // SpatialSubdivision.cs:416
     if (bt.k >= 0 && rf_tri < bs.rf) {
         const TriRec* t = m.tris + bt.k;
@@ -1256,7 +1338,7 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
 __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const DevScene& sc, const DevInstance* __restrict__ insts,
                                                      const double* __restrict__ offsets, const d3* starts, const d3* dirs_view_or_world,
                                                      bool dirs_are_view, Counters* c, XCounters* xc, unsigned int* n_shadow,
-                                                     unsigned int* n_secondary, bool* hit_out)
+                                                     unsigned int* n_secondary, bool* hit_out, bool sync, bool valid)
 {
     PixelOut out; out.color = f.background; out.id = -1;
     Hit h; int which = 0; bool hit = false;
@@ -1264,7 +1346,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
     if (f.n_instances == 1) {
         const DevInstance& in = insts[0];
         dir0 = dirs_are_view ? mul3x3(in.Minv, dirs_view_or_world[0]) : dirs_view_or_world[0];
-        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, xc);
+        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, xc, sync);
     } else {
         // extension: nearest hit across instances, ties to the lowest instance.  Rigid
         // transforms keep |dir|, so every instance's rayFrac is the parameter along dirs_view_or_world[0]
@@ -1306,7 +1388,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
                         const d3 d = mul3x3(in.Minv, dv);
                         Hit hi;
                         if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]),
-                                        d, &hi, xc) &&
+                                        d, &hi, xc, false) &&
                             (hi.rf < best || (hi.rf == best && i < which))) {
                             best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
                             tr.tcull = __double2float_ru(best) * 1.00002f + 1e-6f;
@@ -1322,7 +1404,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
                 const d3 d = mul3x3(in.Minv, dv);
                 Hit hi;
                 if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]), d, &hi,
-                                xc) &&
+                                xc, false) &&
                     hi.rf < best) {
                     best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
                 }
@@ -1330,7 +1412,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
         }
     }
     *hit_out = hit;
-    if (!hit) return out;
+    if (!hit || !valid) return out;
     const DevInstance& in = insts[which];
     const DevMesh& m = sc.meshes[in.mesh];
     out.id = h.id >= 0 ? in.tri_base + h.id : h.id;
@@ -1349,7 +1431,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
         const d3 rs = vadd(h.pos, vscale(h.normal, 0.001));
         (*n_secondary)++;
         Hit h2;
-        if (!closest_hit(sc, m, f.subdivision, f.filter_mode, rs, r, &h2, xc)) { tail = f.background; have_tail = true; break; }
+        if (!closest_hit(sc, m, f.subdivision, f.filter_mode, rs, r, &h2, xc, false)) { tail = f.background; have_tail = true; break; }
         h = h2; d = r;
         depth++;
     }
@@ -1361,9 +1443,9 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
 }
 
 #ifndef SR_MIN_BLOCKS
-#define SR_MIN_BLOCKS 6     // 6 x 128 threads x 85 registers: measured best over the four big configs (profiles/)
+#define SR_MIN_BLOCKS (768 / SR_THREADS)     // 768 threads x 85 registers per SM: measured best over the four big configs (profiles/)
 #endif
-__global__ void __launch_bounds__(128, SR_MIN_BLOCKS)
+__global__ void __launch_bounds__(SR_THREADS, SR_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevScene sc, const DevInstance* __restrict__ g_insts, const double* __restrict__ g_offsets,
               uint32_t* __restrict__ pixels, int32_t* __restrict__ hit_ids, unsigned int* __restrict__ tile_counter,
               DevCounters* __restrict__ counters)
@@ -1381,7 +1463,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     }
     __syncthreads();
 
-    __shared__ int s_acc[4][32][4];           // per warp, per pixel of its tile: sums of R, G, B and the hit id
+    __shared__ int s_acc[SR_THREADS / 32][32][4];           // per warp, per pixel of its tile: sums of R, G, B and the hit id
     const int lane = threadIdx.x & 31;
     const int W = f.width, H = f.height, n = f.sub_pixel_res;
     const int n_tiles = f.tiles_x * f.tiles_y;
@@ -1394,25 +1476,27 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     xc.filter_mismatch = 0;
     unsigned int n_primary = 0, n_shadow = 0, n_secondary = 0, n_hits = 0;
 
-#ifdef SR_BLOCK_SYNC
+    // phase synchronisation (uniform over the launch): the warps of a block take consecutive tiles and start them
+    // together.  Every warp takes part in every barrier: one without a tile repeats the last tile and discards the
+    // result (into xc_void).
     __shared__ int s_tile_base;
-#endif
+    const bool sync = f.phase_sync != 0;
+    XCounters xc_void = xc;
     for (;;) {
         int tile = 0;
-#ifdef SR_BLOCK_SYNC
-        // the 4 warps of a block take 4 consecutive tiles and start them together: they then run the same
-        // code at about the same time, which the instruction cache likes
-        __syncthreads();
-        if (threadIdx.x == 0) s_tile_base = (int)atomicAdd(tile_counter, 4u);
-        __syncthreads();
-        if (s_tile_base >= n_tiles) break;
-        tile = s_tile_base + (int)(threadIdx.x >> 5);
-        if (tile >= n_tiles) continue;
-#else
-        if (lane == 0) tile = (int)atomicAdd(tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
-#endif
+        bool tile_valid = true;
+        if (sync) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_tile_base = (int)atomicAdd(tile_counter, (unsigned int)(SR_THREADS / 32));
+            __syncthreads();
+            if (s_tile_base >= n_tiles) break;
+            tile = s_tile_base + (int)(threadIdx.x >> 5);
+            if (tile >= n_tiles) { tile = n_tiles - 1; tile_valid = false; }
+        } else {
+            if (lane == 0) tile = (int)atomicAdd(tile_counter, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= n_tiles) break;
+        }
         const int ty = tile / f.tiles_x, tx = tile - ty * f.tiles_x;
         const int band_j = ty / f.tiles_per_band;
         const int row0 = f.start_row + (f.band_index + band_j * f.band_count) * f.band_height;
@@ -1432,7 +1516,9 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
             const int col = tx * 8 + (px & 7);
             const int band_r = band_r0 + (px >> 3);
             const int row = row0 + band_r;
-            if (col >= W || band_r >= f.band_height || row > f.end_row) continue;
+            const bool valid = tile_valid && !(col >= W || band_r >= f.band_height || row > f.end_row);
+            if (!sync && !valid) continue;
+            SR_SYNC_POINT(sync);
             const int sx = si / n, sy = si - sx * n;                                      // subX outer, subY inner (:1762-1764)
             double fx = 0.0, fy = 0.0;                                                    // n == 1: (col + 0.0) / W == col / W
             if (n > 1) {
@@ -1457,10 +1543,11 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
                          dmul(-dsub(ddiv(dadd((double)row, fy), (double)H), 0.5), f.aspect), f.fov_depth);   // :1728, :1794-1796
                 is_view = true;
             }
-            n_primary++;
+            if (valid) n_primary++;
             bool hit = false;
-            const PixelOut s1 = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, &xc, &n_shadow, &n_secondary,
-                                                 &hit);
+            const PixelOut s1 = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, valid ? &xc : &xc_void, &n_shadow,
+                                                 &n_secondary, &hit, sync, valid);
+            if (!valid) continue;
             if (hit) n_hits++;
             int* pa = s_acc[threadIdx.x >> 5][px];
             if (nn == 1) {
@@ -1477,7 +1564,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
             const int col = tx * 8 + (lane & 7);
             const int band_r = band_r0 + (lane >> 3);
             const int row = row0 + band_r;
-            if (col < W && band_r < f.band_height && row <= f.end_row) {
+            if (tile_valid && col < W && band_r < f.band_height && row <= f.end_row) {
                 const int sum_r = acc[0] / nn, sum_g = acc[1] / nn, sum_b = acc[2] / nn;  // :1820-1822
                 const size_t idx = (size_t)row * (size_t)W + (size_t)col;
                 pixels[idx] = 0xff000000u | ((uint32_t)(sum_r & 0xff) << 16) | ((uint32_t)(sum_g & 0xff) << 8) |
@@ -1512,14 +1599,14 @@ cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstan
         cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    render_kernel<<<grid_blocks, 128, smem, stream>>>(f, sc, d_insts, d_offsets, d_pixels, d_ids, d_tile_counter, d_counters);
+    render_kernel<<<grid_blocks, SR_THREADS, smem, stream>>>(f, sc, d_insts, d_offsets, d_pixels, d_ids, d_tile_counter, d_counters);
     return cudaGetLastError();
 }
 
 int render_kernel_occupancy(int smem_bytes)
 {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel, 128, (size_t)smem_bytes) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel, SR_THREADS, (size_t)smem_bytes) != cudaSuccess) return 0;
     return nb;
 }
 

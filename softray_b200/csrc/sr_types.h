@@ -129,7 +129,8 @@ struct DevFrame {
     int32_t filter_mode;        // SOFTRAY_FILTER_*: 0 filter + exact fallback, 1 exact only, 2 verify
     float   light_radius;       // >= the length of every area-light offset (0.2, ShadowMethod.cs:10), rounded up
     int32_t bundle_budget;      // node visits a shadow-bundle cone walk may spend before giving up (0 = no bundles)
-    int32_t _pad;
+    int32_t phase_sync;         // 1: the warps of a block meet at barriers between the stages of a camera ray
+                                // (sr_render.cu "Phase synchronisation"); 0: they run free
     // composite frames (n_instances > 1): a BVH over the view-space boxes of the instances, rebuilt per frame
     const BvhNode* tlas_nodes;  // leaf primitives index tlas_order
     const int32_t* tlas_order;  // instance index of the k-th TLAS leaf primitive
