@@ -483,3 +483,29 @@ def test_handles_may_be_released_in_any_order(lib, obj_mesh):
     out = lib.Scene(c2, [obj_mesh]).render(scenario(resolution=16))
     assert (out["pixels"] >> 24 == 0xFF).all()
     c2.close()
+
+
+def test_phase_sync_changes_nothing(lib, ctx, obj_mesh, monkeypatch):
+    """Stage barriers (sr_render.cu "Phase synchronisation") only change WHEN warps run what: frames, hit ids and
+    every counter must be identical with them forced on and off -- including frames whose tiles do not fill the
+    last block (warps without a tile), widths / heights that are not multiples of the 8x4 tile (lanes without a
+    pixel), supersampling, focal blur, shadows, mirror bounces and spheres."""
+    meshes2, spheres2, p2 = synth.config2(width=203, height=117, shadow_samples=16, n_spheres=300)
+    meshes3, _, p3 = synth.config3(width=150, height=85, nx=101, nz=51, shadow_samples=3)
+    jobs = [([obj_mesh], None, scenario(resolution=100, shadows=True)),
+            ([obj_mesh], None, scenario(width=77, height=53, sub_pixel_res=2)),
+            ([obj_mesh], None, scenario(width=90, height=61, sub_pixel_res=2, focal_blur=True, start_row=7, end_row=49)),
+            ([obj_mesh], path_trace_spheres(), scenario(resolution=64, shadows=True, shadow_samples=5)),
+            (meshes2, spheres2, p2), (meshes3, None, p3)]
+    for meshes, sph, p in jobs:
+        sc = lib.Scene(ctx, meshes, sph)
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("SOFTRAY_PHASE_SYNC", mode)
+            out[mode] = sc.render(p, want_ids=True)
+        a, b = out["0"], out["1"]
+        assert np.array_equal(a["pixels"], b["pixels"]) and np.array_equal(a["ids"], b["ids"])
+        for k in ("rays_primary", "rays_shadow", "rays_secondary", "hits_primary", "shaded_hits", "node_visits", "prim_tests",
+                  "sphere_tests", "filter_tests", "filter_unsure", "rays_bundled"):
+            assert getattr(a["stats"], k) == getattr(b["stats"], k), k
+        sc.close()
