@@ -331,14 +331,13 @@ def main():
                 scene.render(frame, pixels=hp, want_stats=False)
             e2e_ms = (time.perf_counter() - t) * 1e3 / e2e_steps
         else:
-            fb_view = _as_tensor(peer.ptr, H, W) if (peer is not None and rank == 0) else None
+            # the caller's surface is one shared-memory section every rank process maps and page-locks: each rank's
+            # softray_render stores its bands straight into it over its own GPU's PCIe link (multi_gpu "host" variant)
+            shared = multi_gpu.SharedHostFramebuffer(W, H, ctx=ctx)
 
             def e2e_step():
-                assembled = step_device()           # nccl: rank 0 gets the gathered frame
-                barrier()                           # every band has landed in rank 0's HBM
-                if rank == 0:
-                    host_px.copy_(fb_view if fb_view is not None else assembled)
-                    torch.cuda.synchronize()
+                scene.render(frame, pixels=shared.pixels, want_stats=False)     # returns when this rank's bands are in host memory
+                shared.barrier()                                                # ... and now everybody's are (softray_host_barrier)
 
             for _ in range(2):
                 e2e_step()
@@ -346,17 +345,26 @@ def main():
             t = time.perf_counter()
             for _ in range(e2e_steps):
                 e2e_step()
-            barrier()
             e2e_ms = (time.perf_counter() - t) * 1e3 / e2e_steps
             tt = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_ms = float(tt.item())
+            e2e_ok = None
+            if rank == 0:      # the assembled host surface equals the device-side gather of the timed region
+                if peer is not None:
+                    ref = _as_tensor(peer.ptr, H, W).cpu().numpy().view(np.uint32)
+                    e2e_ok = bool(np.array_equal(ref, shared.pixels))
+            shared.close()
         # frame constants uploaded per call: DevInstance records + the area-light offsets
         h2d = 288 * len(frame.instances) + (24 * frame.shadow_samples if frame.shadows else 0)
         e2e = {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": W * H * 4,
                "note": "softray_render (C ABI) with a pinned host framebuffer, which the kernel writes directly over PCIe (zero-copy stores: the D2H bytes leave the GPU while tracing continues); the scene is resident "
-                       "(uploaded once by softray_scene_create, like the reference caches its geometry)"}
+                       "(uploaded once by softray_scene_create, like the reference caches its geometry)"
+                       + ("; N > 1: the host surface is a shared-memory section every rank maps and page-locks, each GPU writes its own "
+                          "row bands into it over its own PCIe link, a frame ends with a barrier" if world > 1 else "")}
+        if world > 1 and rank == 0:
+            e2e["matches_device_gather"] = e2e_ok
 
     # ---- roofline of the render kernel: FP issue (branchy FP32 search + FP64 reference arithmetic; not
     # HBM-bound, not tensor work).  Mixed-precision rule of SURVEY 8d: FP32 work against the measured

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SOFTRAY_ABI_VERSION 2
+#define SOFTRAY_ABI_VERSION 3
 #define SOFTRAY_MAX_INSTANCES 128   /* instances per frame (composite extension) */
 #define SOFTRAY_MAX_SHADOW_SAMPLES 1024
 
@@ -233,6 +233,18 @@ int  softray_device_free(softray_ctx* ctx, void* d_ptr);
 int  softray_ipc_export(softray_ctx* ctx, void* d_ptr /* from softray_device_alloc */, char handle[SOFTRAY_IPC_HANDLE_BYTES]);
 int  softray_ipc_open(softray_ctx* ctx, const char handle[SOFTRAY_IPC_HANDLE_BYTES], void** d_ptr_out);
 int  softray_ipc_close(softray_ctx* ctx, void* d_ptr);
+
+/* Page-lock a caller-owned host framebuffer (C#: the pinned `int[] surface.Pixels`, Surface.cs:20-30; or a
+ * shared-memory section several rank processes map) so that softray_render's kernel stores finished pixels
+ * straight into it over PCIe -- no device framebuffer, no D2H copy, and with one process per GPU every GPU
+ * writes its own row bands into the one host surface over its own PCIe link (the multi-GPU gather of the
+ * host-buffer path).  Optional: an unregistered buffer takes the staged copy.  Unregister before freeing. */
+int  softray_host_register(softray_ctx* ctx, void* host_ptr, uint64_t n_bytes);
+int  softray_host_unregister(softray_ctx* ctx, void* host_ptr);
+/* End-of-frame rendezvous of the rank processes that share a host surface: a sense-reversing spin barrier on two
+ * uint32 words (zero-initialised by their owner) in memory all of them map.  Returns when n_ranks callers arrived;
+ * no CUDA involved (the rank's own softray_render has already returned, i.e. its bands are in host memory). */
+int  softray_host_barrier(volatile uint32_t* two_words, uint32_t n_ranks);
 
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Measured FMA-issue peak of the context's device in TFLOP/s (FMA = 2 flops): the denominator of

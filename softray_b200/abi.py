@@ -5,7 +5,7 @@ against the values the C side reports through softray_abi_sizeof().
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK = 0
 E_INVALID_ARG = -1

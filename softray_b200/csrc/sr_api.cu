@@ -1106,6 +1106,44 @@ extern "C" int softray_ipc_open(softray_ctx* ctx, const char handle[SOFTRAY_IPC_
     return SOFTRAY_OK;
 }
 
+extern "C" int softray_host_register(softray_ctx* ctx, void* host_ptr, uint64_t n_bytes)
+{
+    if (!ctx || !host_ptr || n_bytes == 0) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_host_register: NULL argument");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    SR_CUDA(ctx, cudaHostRegister(host_ptr, (size_t)n_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_host_unregister(softray_ctx* ctx, void* host_ptr)
+{
+    if (!ctx || !host_ptr) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_host_unregister: NULL argument");
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->stream) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SR_CUDA(ctx, cudaHostUnregister(host_ptr));
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_host_barrier(volatile uint32_t* w, uint32_t n_ranks)
+{
+    if (!w || n_ranks == 0) return fail(nullptr, SOFTRAY_E_INVALID_ARG, "softray_host_barrier: NULL argument");
+    uint32_t* count = const_cast<uint32_t*>(w);
+    uint32_t* generation = const_cast<uint32_t*>(w) + 1;
+    const uint32_t gen = __atomic_load_n(generation, __ATOMIC_ACQUIRE);
+    if (__atomic_add_fetch(count, 1u, __ATOMIC_ACQ_REL) == n_ranks) {
+        __atomic_store_n(count, 0u, __ATOMIC_RELAXED);
+        __atomic_add_fetch(generation, 1u, __ATOMIC_RELEASE);
+    } else {
+        unsigned long long spins = 0;
+        while (__atomic_load_n(generation, __ATOMIC_ACQUIRE) == gen) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if ((++spins & 0xfffff) == 0) std::this_thread::yield();     // a rank that lost its core must not starve the others
+        }
+    }
+    return SOFTRAY_OK;
+}
+
 extern "C" int softray_ipc_close(softray_ctx* ctx, void* d_ptr)
 {
     if (!ctx || !d_ptr) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_ipc_close: NULL argument");

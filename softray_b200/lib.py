@@ -29,6 +29,7 @@ EXPORTS = [
     "softray_scene_create", "softray_scene_destroy", "softray_scene_fingerprint",
     "softray_render", "softray_render_device", "softray_instance_init", "softray_frame_defaults",
     "softray_device_alloc", "softray_device_free", "softray_ipc_export", "softray_ipc_open", "softray_ipc_close",
+    "softray_host_register", "softray_host_unregister", "softray_host_barrier",
     "softray_measure_fma_peak", "softray_model_load_3ds", "softray_model_get_mesh", "softray_model_destroy",
     "softray_resolve", "softray_resolve_device",
 ]
@@ -95,6 +96,9 @@ def load():
     L.softray_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.softray_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.softray_ipc_close.argtypes = [vp, vp]
+    L.softray_host_register.argtypes = [vp, vp, C.c_uint64]
+    L.softray_host_unregister.argtypes = [vp, vp]
+    L.softray_host_barrier.argtypes = [vp, C.c_uint32]
     L.softray_resolve.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, vp]
     L.softray_resolve_device.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, vp, vp]
     L.softray_model_load_3ds.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(vp)]
@@ -200,6 +204,13 @@ class Context:
         out = C.c_void_p()
         _check(load().softray_ipc_open(self._h, handle_bytes, C.byref(out)), self._h, "softray_ipc_open")
         return out.value
+
+    def host_register(self, array):
+        """softray_host_register on a numpy array's memory (page-lock it for zero-copy frames)."""
+        _check(load().softray_host_register(self._h, C.c_void_p(array.ctypes.data), int(array.nbytes)), self._h, "softray_host_register")
+
+    def host_unregister(self, array):
+        _check(load().softray_host_unregister(self._h, C.c_void_p(array.ctypes.data)), self._h, "softray_host_unregister")
 
     def ipc_close(self, device_ptr):
         _check(load().softray_ipc_close(self._h, C.c_void_p(device_ptr)), self._h, "softray_ipc_close")

@@ -12,6 +12,10 @@ surface.Pixels (Renderer.cs:1655-1680) and exposes rayTraceStartRow/EndRow for c
   * nccl : every rank renders into a local frame, packs its rows and torch.distributed.gather
     moves them to rank 0 (NCCL send/recv over NVLink; gloo on CPU in the tests).
 
+  * host  (the host-buffer entry point, softray_render): the caller's surface lives in a shared-memory section
+    every rank process maps and page-locks (softray_host_register); each rank's kernel stores its bands straight
+    into it over its own GPU's PCIe link -- no device framebuffer, no NVLink hop, no D2H copy on rank 0.
+
 Only host-side logic lives here; torch.distributed is plumbing.
 """
 import numpy as np
@@ -109,3 +113,69 @@ class PeerFramebuffer:
             else:
                 self.ctx.ipc_close(self.ptr)
             self.ptr = None
+
+
+class SharedHostFramebuffer:
+    """host variant: one width*height uint32 surface in POSIX shared memory, mapped by every rank process.
+    .pixels is the [H, W] uint32 numpy view to pass to Scene.render(..., pixels=...) on THIS rank; with a
+    Context it is page-locked in this process (softray_host_register) so the kernel writes it directly."""
+
+    def __init__(self, width, height, ctx=None, group=None):
+        from multiprocessing import shared_memory
+
+        import torch.distributed as dist
+
+        self.ctx = ctx
+        self.rank = dist.get_rank(group)
+        self.owner = self.rank == 0
+        nbytes = int(width) * int(height) * 4
+        self.world = dist.get_world_size(group)
+        box = [None]
+        if self.owner:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes + 64)     # + the barrier words
+            box[0] = self.shm.name
+        dist.broadcast_object_list(box, src=0, group=group)
+        if not self.owner:
+            self.shm = shared_memory.SharedMemory(name=box[0])
+            try:    # the owner unlinks; keep Python's resource tracker from doing it again at exit
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.pixels = np.ndarray((int(height), int(width)), dtype=np.uint32, buffer=self.shm.buf)
+        self._words = np.ndarray((2,), dtype=np.uint32, buffer=self.shm.buf, offset=nbytes)
+        if self.owner:
+            self.pixels[:] = 0
+            self._words[:] = 0
+        self.registered = False
+        if ctx is not None:
+            ctx.host_register(self.pixels)
+            self.registered = True
+        dist.barrier(group)
+        self.group = group
+
+    def barrier(self):
+        """End of frame: every rank's softray_render has returned (softray_host_barrier, a spin barrier in the
+        shared section; needs the library)."""
+        from . import lib
+
+        rc = lib.load().softray_host_barrier(self._words.ctypes.data, self.world)
+        if rc != 0:
+            raise RuntimeError("softray_host_barrier failed")
+
+    def close(self):
+        import torch.distributed as dist
+
+        if getattr(self, "shm", None) is None:
+            return
+        if self.registered:
+            self.ctx.host_unregister(self.pixels)
+            self.registered = False
+        dist.barrier(self.group)
+        self.pixels = None
+        self._words = None
+        self.shm.close()
+        if self.owner:
+            self.shm.unlink()
+        self.shm = None

@@ -86,3 +86,41 @@ def test_default_band_height_is_a_tile_multiple():
             bh = multi_gpu.default_band_height(h, w)
             assert bh % 4 == 0 and bh >= 4
     assert multi_gpu.default_band_height(1080, 1) == 0
+
+
+def _shared_worker(rank, world, port, band_height, res, out_path):
+    import torch.distributed as dist
+
+    import oracle
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_fixtures.npz"))
+        mesh = oracle.load_3ds(fx["model/obj.3ds"].tobytes())
+        params = scenario(resolution=res, shadows=False)
+        multi_gpu.apply_partition(params, rank, world, band_height)
+        shared = multi_gpu.SharedHostFramebuffer(res, res)          # no Context: not page-locked on CPU
+        oracle.Scene([mesh]).render(params, pixels=shared.pixels)   # every rank writes its own bands only
+        for _ in range(200):                                        # the library's spin barrier, many generations
+            shared.barrier()
+        if rank == 0:
+            np.save(out_path, shared.pixels.copy())
+        shared.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,band_height", [(2, 8), (3, 4)])
+def test_shared_host_framebuffer_collects_every_rank(tmp_path, obj_mesh, world, band_height):
+    """multi_gpu "host" variant: the ranks' bands land in one shared-memory surface (bench.py's e2e at N > 1)."""
+    import torch.multiprocessing as mp
+
+    import oracle
+
+    res = 48
+    out = str(tmp_path / "shared.npy")
+    mp.spawn(_shared_worker, args=(world, _free_port(), band_height, res, out), nprocs=world, join=True)
+    want = oracle.Scene([obj_mesh]).render(scenario(resolution=res, shadows=False))["pixels"]
+    assert np.array_equal(np.load(out), want)
