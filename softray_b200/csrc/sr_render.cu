@@ -1050,7 +1050,7 @@ __device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivisio
 
 // IRayIntersectable.IntersectRay of rootGeometry for a camera / reflection ray: the nearest hit.
 __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, int filter_mode, d3 s, d3 dir,
-                                            Hit* h, XCounters* c, bool sync)
+                                            Hit* h, XCounters* c, int sync)
 {
     // --- spheres (tested first in list order) ---
     BestPrim bs; bs.rf = kNoHit; bs.k = -1; bs.index = 0x7fffffff;
@@ -1064,7 +1064,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
             known = spheres_filter<false>(sc, s, dir, list, &n_list, &nv, &nf, c->stack);
             c->node_visits += nv; c->filter_tests += nf;
         }
-        SR_SYNC_POINT(sync);
+        SR_SYNC_POINT(sync & 2);
         const bool listed = known == 2 && n_list >= 1 && n_list <= kMaxCand;
         if (filter_mode == 2) {
             spheres_closest_exact(sc, s, dirn, nullptr, 0, &bs, c);
@@ -1080,7 +1080,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
             spheres_closest_exact(sc, s, dirn, nullptr, 0, &bs, c);
         }
     }
-    SR_SYNC_POINT(sync);
+    SR_SYNC_POINT(sync & 4);
     // --- mesh ---
     BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
     d3 ts = s; double offset = 0.0;
@@ -1104,7 +1104,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
                 }
             }
         }
-        SR_SYNC_POINT(sync);
+        SR_SYNC_POINT(sync & 8);
         if (filter_mode == 2) {
             mesh_closest_exact(m, subdivision, s, dir, nullptr, 0, &bt, &ts, &offset, c);
             bool in_list = bt.k < 0;
@@ -1122,7 +1122,7 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
             mesh_closest_exact(m, subdivision, s, dir, nullptr, 0, &bt, &ts, &offset, c);
         }
     }
-    SR_SYNC_POINT(sync);
+    SR_SYNC_POINT(sync & 16);
     const double rf_tri = bt.k >= 0 ? dadd(bt.rf, offset) : kNoHit;   // SpatialSubdivision.cs:416
     if (bt.k >= 0 && rf_tri < bs.rf) {
         const TriRec* t = m.tris + bt.k;
@@ -1346,7 +1346,7 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
 __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const DevScene& sc, const DevInstance* __restrict__ insts,
                                                      const double* __restrict__ offsets, const d3* starts, const d3* dirs_view_or_world,
                                                      bool dirs_are_view, Counters* c, XCounters* xc, unsigned int* n_shadow,
-                                                     unsigned int* n_secondary, bool* hit_out, bool sync, bool valid)
+                                                     unsigned int* n_secondary, bool* hit_out, int sync, bool valid)
 {
     PixelOut out; out.color = f.background; out.id = -1;
     Hit h; int which = 0; bool hit = false;
@@ -1488,7 +1488,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     // together.  Every warp takes part in every barrier: one without a tile repeats the last tile and discards the
     // result (into xc_void).
     __shared__ int s_tile_base;
-    const bool sync = f.phase_sync != 0;
+    const int sync = f.phase_sync;             // bit 0: tile fetch + start of a camera ray; bits 1-4: the stages of closest_hit
     XCounters xc_void = xc;
     for (;;) {
         int tile = 0;
@@ -1526,7 +1526,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
             const int row = row0 + band_r;
             const bool valid = tile_valid && !(col >= W || band_r >= f.band_height || row > f.end_row);
             if (!sync && !valid) continue;
-            SR_SYNC_POINT(sync);
+            SR_SYNC_POINT(sync & 1);
             const int sx = si / n, sy = si - sx * n;                                      // subX outer, subY inner (:1762-1764)
             double fx = 0.0, fy = 0.0;                                                    // n == 1: (col + 0.0) / W == col / W
             if (n > 1) {

@@ -501,7 +501,7 @@ def test_phase_sync_changes_nothing(lib, ctx, obj_mesh, monkeypatch):
         sc = lib.Scene(ctx, meshes, sph)
         out = {}
         for mode in ("0", "1"):
-            monkeypatch.setenv("SOFTRAY_PHASE_SYNC", mode)
+            monkeypatch.setenv("SOFTRAY_PHASE_SYNC", {"0": "0", "1": "31"}[mode])
             out[mode] = sc.render(p, want_ids=True)
         a, b = out["0"], out["1"]
         assert np.array_equal(a["pixels"], b["pixels"]) and np.array_equal(a["ids"], b["ids"])
