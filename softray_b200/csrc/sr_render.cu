@@ -32,6 +32,16 @@ namespace sr {
 #ifndef SR_THREADS
 #define SR_THREADS 256
 #endif
+// closest_hit used to be out of line (code size): its Hit result and counters then travel through local memory.
+// Inlined: config2 0.638 -> 0.590, config3 47.0 -> 46.0, config4 222 -> 181, config5 16.5 -> 15.1 ms.
+#ifndef SR_CH_INLINE
+#define SR_CH_INLINE __forceinline__
+#endif
+// ... and so did the exact evaluators' results (BestPrim, clipped start, offset), once they had a single call
+// site each: config2 0.582 -> 0.537, config4 173 -> 166 ms.
+#ifndef SR_EX_INLINE
+#define SR_EX_INLINE __forceinline__
+#endif
 #ifndef SR_PREFETCH
 #define SR_PREFETCH 1     // prefetch the far child when both are hit: config3 47.6 -> 46.6, config4 223 -> 218 ms
 #endif
@@ -981,7 +991,7 @@ struct Hit {
 constexpr double kNoHit = 1.7976931348623157e308;   // double.MaxValue (GeometryCollection.cs:48)
 
 // Exact (reference arithmetic) nearest sphere / nearest triangle.
-__device__ __noinline__ void spheres_closest_exact(const DevScene& sc, d3 s, d3 dirn, const int* list, int n_list, BestPrim* bs,
+__device__ SR_EX_INLINE void spheres_closest_exact(const DevScene& sc, d3 s, d3 dirn, const int* list, int n_list, BestPrim* bs,
                                                    XCounters* c)
 {
     if (n_list > 0) {       // only the spheres the filter could not rule out
@@ -1007,7 +1017,7 @@ __device__ __noinline__ void spheres_closest_exact(const DevScene& sc, d3 s, d3 
 }
 
 // n_list > 0: only the listed triangles (the filter has proven every other one missed or beaten)
-__device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivision, d3 s, d3 dir, const int* list, int n_list,
+__device__ SR_EX_INLINE void mesh_closest_exact(const DevMesh& m, int subdivision, d3 s, d3 dir, const int* list, int n_list,
                                                 BestPrim* bt, d3* ts_out, double* offset_out, XCounters* c)
 {
     d3 ts = s; double offset = 0.0;
@@ -1049,7 +1059,7 @@ __device__ __noinline__ void mesh_closest_exact(const DevMesh& m, int subdivisio
 }
 
 // IRayIntersectable.IntersectRay of rootGeometry for a camera / reflection ray: the nearest hit.
-__device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, int filter_mode, d3 s, d3 dir,
+__device__ SR_CH_INLINE bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, int filter_mode, d3 s, d3 dir,
                                             Hit* h, XCounters* c, int sync)
 {
     // --- spheres (tested first in list order) ---
@@ -1066,18 +1076,19 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
         }
         SR_SYNC_POINT(sync & 2);
         const bool listed = known == 2 && n_list >= 1 && n_list <= kMaxCand;
-        if (filter_mode == 2) {
-            spheres_closest_exact(sc, s, dirn, nullptr, 0, &bs, c);
+        const bool verify = filter_mode == 2;
+        const bool use_list = listed && !verify;
+        // one call site (the function is inlined): the listed spheres, or all of them (VERIFY; an undecided filter)
+        if (verify || known == 2) spheres_closest_exact(sc, s, dirn, use_list ? list : nullptr, use_list ? n_list : 0, &bs, c);
+        if (verify) {
             bool in_list = bs.k < 0 || !listed;
             for (int j = 0; listed && j < n_list; j++) in_list = in_list || list[j] == bs.k;
             if ((known == 0 && bs.k >= 0) || !in_list) c->filter_mismatch++;
             if (known == 2 && n_list != 1) c->filter_unsure++;
         } else if (listed) {
             if (n_list > 1) c->filter_unsure++;
-            spheres_closest_exact(sc, s, dirn, list, n_list, &bs, c);
         } else if (known == 2) {
             if (filter_mode != 1 && sc.sphere_nodes != nullptr) c->filter_unsure++;
-            spheres_closest_exact(sc, s, dirn, nullptr, 0, &bs, c);
         }
     }
     SR_SYNC_POINT(sync & 4);
@@ -1105,8 +1116,12 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
             }
         }
         SR_SYNC_POINT(sync & 8);
-        if (filter_mode == 2) {
-            mesh_closest_exact(m, subdivision, s, dir, nullptr, 0, &bt, &ts, &offset, c);
+        const bool verify = filter_mode == 2;
+        const bool use_list = known == 1 && !verify;
+        // one call site (the function is inlined): the candidates, or the full exact walk (VERIFY; an undecided filter)
+        if (verify || known != 0)
+            mesh_closest_exact(m, subdivision, s, dir, use_list ? list : nullptr, use_list ? n_list : 0, &bt, &ts, &offset, c);
+        if (verify) {
             bool in_list = bt.k < 0;
             for (int j = 0; j < n_list; j++) in_list = in_list || list[j] == bt.k;
             // contradictions: "surely nothing" but the exact walk hits; the exact winner is not a candidate;
@@ -1116,10 +1131,8 @@ __device__ __noinline__ bool closest_hit(const DevScene& sc, const DevMesh& m, i
             if (known == 2 || n_list > 1) c->filter_unsure++;
         } else if (known == 1) {
             if (n_list > 1) c->filter_unsure++;
-            mesh_closest_exact(m, subdivision, s, dir, list, n_list, &bt, &ts, &offset, c);
         } else if (known == 2) {
             if (filter_mode != 1 && m.nodes != nullptr) c->filter_unsure++;
-            mesh_closest_exact(m, subdivision, s, dir, nullptr, 0, &bt, &ts, &offset, c);
         }
     }
     SR_SYNC_POINT(sync & 16);
