@@ -721,9 +721,12 @@ constexpr int kMaxCand = 4;
 struct FClosest { float best_hi; int best_k; int n_cand; int cand[kMaxCand]; float cand_lo[kMaxCand]; };
 
 __device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ nodes, const TriFilt* __restrict__ filt, int n_tris,
-                                                    FRay& r, float V, FClosest* out, XCounters* c)
+                                                    FRay& r, float V, FClosest* out, XCounters* c, float limit_tau = 1e30f)
 {
-    float best_hi = 1e30f;
+    // limit_tau: hits beyond it are of no use to the caller (a composite frame already has a nearer hit in
+    // another instance): they are culled like hits behind a sure hit
+    float best_hi = limit_tau;
+    r.tcull = fminf(r.tcull, limit_tau * 1.00002f + 1e-6f);
     int best_k = -1;
     int n_cand = 0;
     int c0 = -1, c1 = -1, c2 = -1, c3 = -1;
@@ -1059,8 +1062,9 @@ __device__ SR_EX_INLINE void mesh_closest_exact(const DevMesh& m, int subdivisio
 }
 
 // IRayIntersectable.IntersectRay of rootGeometry for a camera / reflection ray: the nearest hit.
+// limit: mesh hits with a rayFrac beyond it cannot matter to the caller (kNoHit: none).  Only prunes the search.
 __device__ SR_CH_INLINE bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, int filter_mode, d3 s, d3 dir,
-                                            Hit* h, XCounters* c, int sync)
+                                            Hit* h, XCounters* c, int sync, double limit = 1.7976931348623157e308)
 {
     // --- spheres (tested first in list order) ---
     BestPrim bs; bs.rf = kNoHit; bs.k = -1; bs.index = 0x7fffffff;
@@ -1105,7 +1109,11 @@ __device__ SR_CH_INLINE bool closest_hit(const DevScene& sc, const DevMesh& m, i
             known = fray_setup_fwd(m, subdivision, s, dir, &r, &t0);
             if (known == 1) {
                 FClosest fc;
-                walk_filter_closest(m.nodes, m.filt, m.n_tris, r, m.scale, &fc, c);
+                // rayFrac = t0 + tau, so tau <= limit - t0 (rounded up) keeps every hit that can still win or tie
+                // (a sphere already hit limits it too: a triangle wins only with a SMALLER rayFrac, GeometryCollection.cs:53)
+                const double lim = (filter_mode != 2 && bs.k >= 0 && bs.rf < limit) ? bs.rf : limit;
+                const float limit_tau = lim < 1e300 ? __double2float_ru(lim - t0) * (1.0f + 4.0f * kU) + 1e-6f : 1e30f;
+                walk_filter_closest(m.nodes, m.filt, m.n_tris, r, m.scale, &fc, c, limit_tau);
                 sure_hit = fc.best_k >= 0;
                 if (fc.n_cand == 0) known = 0;
                 else if (fc.n_cand > kMaxCand) known = 2;
@@ -1409,7 +1417,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
                         const d3 d = mul3x3(in.Minv, dv);
                         Hit hi;
                         if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]),
-                                        d, &hi, xc, false) &&
+                                        d, &hi, xc, false, f.filter_mode == 2 ? kNoHit : best) &&
                             (hi.rf < best || (hi.rf == best && i < which))) {
                             best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
                             tr.tcull = __double2float_ru(best) * 1.00002f + 1e-6f;
@@ -1425,7 +1433,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
                 const d3 d = mul3x3(in.Minv, dv);
                 Hit hi;
                 if (closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, mk(in.start[0], in.start[1], in.start[2]), d, &hi,
-                                xc, false) &&
+                                xc, false, f.filter_mode == 2 ? kNoHit : best) &&
                     hi.rf < best) {
                     best = hi.rf; h = hi; which = i; hit = true; dir0 = d;
                 }
