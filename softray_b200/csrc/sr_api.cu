@@ -109,6 +109,7 @@ static int cuda_fail(softray_ctx* ctx, cudaError_t e, const char* what)
     const int code = (e == cudaErrorMemoryAllocation) ? SOFTRAY_E_OOM
                      : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? SOFTRAY_E_NO_DEVICE
                                                                                                                    : SOFTRAY_E_CUDA;
+    cudaGetLastError();     // the runtime remembers a failed call until asked: the next launch check must not see it
     return fail(ctx, code, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
 

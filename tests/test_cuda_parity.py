@@ -9,7 +9,7 @@ import math
 import numpy as np
 import pytest
 
-from softray_b200 import FrameParams, InstanceData, MeshData, SphereData, abi, synth
+from softray_b200 import FrameParams, InstanceData, MeshData, SphereData, abi, multi_gpu, synth
 from tests.util import channel_absdiff, count_diff, golden_name, path_trace_spheres, scenario
 
 pytestmark = pytest.mark.gpu
@@ -381,6 +381,32 @@ def test_pinned_host_framebuffer_is_written_by_the_kernel_itself(obj_scene):
     got = obj_scene.render(p, want_ids=True, pixels=px.numpy().view(np.uint32), ids=ids.numpy())
     assert np.array_equal(got["pixels"], want["pixels"]) and np.array_equal(got["ids"], want["ids"])
     assert (got["pixels"][:11] == 0xABCDEF01).all() and (got["pixels"][141:] == 0xABCDEF01).all()
+
+
+def test_host_register_makes_a_caller_buffer_zero_copy(lib, ctx, obj_scene):
+    """softray_host_register page-locks a caller-owned surface (the pinned int[] of the C# host, or the shared
+    section of the multi-GPU host path): same frame as the staged copy, banded frames write only their bands, and
+    the buffer can be unregistered and used again."""
+    p = scenario(resolution=128, shadows=True, shadow_samples=4)
+    want = obj_scene.render(p)["pixels"]
+    buf = np.full((128, 128), 0x01020304, dtype=np.uint32)
+    ctx.host_register(buf)
+    try:
+        got = obj_scene.render(p, pixels=buf)["pixels"]
+        assert np.array_equal(got, want)
+        buf[:] = 0x01020304
+        multi_gpu.apply_partition(p, 1, 2, 8)              # rank 1 of 2, bands of 8 rows
+        obj_scene.render(p, pixels=buf)
+        rows = multi_gpu.rows_of_rank(128, 2, 8, 1)
+        mask = np.zeros(128, dtype=bool)
+        mask[rows] = True
+        assert np.array_equal(buf[mask], want[mask]) and (buf[~mask] == 0x01020304).all()
+    finally:
+        ctx.host_unregister(buf)
+    multi_gpu.apply_partition(p, 0, 1, 0)
+    assert np.array_equal(obj_scene.render(p, pixels=buf)["pixels"], want)      # staged copy again
+    with pytest.raises(lib.SoftRayError):
+        ctx.host_unregister(buf)                            # not registered any more: CUDA error code, no crash
 
 
 def test_config1_full_size_against_oracle(lib, ctx, fixtures, obj_oracle):
