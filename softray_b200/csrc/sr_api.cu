@@ -366,6 +366,7 @@ inline double sah_isect_cost(double dflt)
 }
 
 constexpr long long kPhaseSyncMaxPrims = 65536;
+constexpr int kPhaseSyncComposite = 0;
 constexpr int kPhaseSyncStages = 3;           // bit 0: tile fetch + ray start; 1: sphere search; 2: exact spheres; 3: mesh search; 4: clip + exact triangles.
                                               // config2 ms: 0 -> 0.717, 1 -> 0.688, 3 -> 0.638, 9 -> 0.640, 19 -> 0.641, 7 -> 0.646, 31 -> 0.654
 constexpr int kBundleMinSamples = 16, kBundleBudget = 384;   // budget counts child boxes: 384 = 192 nodes
@@ -843,13 +844,15 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     // Stage barriers (sr_render.cu "Phase synchronisation") need every thread of a block in every stage: single-
     // instance frames only (a composite frame calls the per-instance search from inside its hierarchy walk).  They pay
     // where instruction fetch, not the walks, bounds the camera rays: a small cache-resident scene (short walks of
-    // similar length) under a frame with enough tiles to keep every warp busy.  SOFTRAY_PHASE_SYNC=<mask> overrides.
+    // similar length) under a frame with at least two tiles per resident warp (config1, 512x512: 0.0586 vs 0.0591 ms, no loss).  SOFTRAY_PHASE_SYNC=<mask> overrides.
     {
         long long prims = scene->dev.n_spheres;
         for (int32_t t : scene->mesh_tris) prims += t;
         const long long tiles = (long long)((f.width + 7) / 8) * ((rows + 3) / 4) / (f.band_count > 0 ? f.band_count : 1);
-        const bool small_scene = prims <= kPhaseSyncMaxPrims && tiles >= 8LL * ctx->sm_count * (768 / 32);
-        f.phase_sync = fr->n_instances == 1 ? env_int("SOFTRAY_PHASE_SYNC", small_scene ? kPhaseSyncStages : 0) : 0;
+        const bool small_scene = prims <= kPhaseSyncMaxPrims && tiles >= 2LL * ctx->sm_count * (768 / 32);
+        // (a composite frame can only have bit 0: tile fetch + start of a camera ray, both outside its hierarchy walk)
+        f.phase_sync = fr->n_instances == 1 ? env_int("SOFTRAY_PHASE_SYNC", small_scene ? kPhaseSyncStages : 0)
+                                            : (env_int("SOFTRAY_PHASE_SYNC", kPhaseSyncComposite) & 1);
         if (f.phase_sync) f.phase_sync |= 1;           // (the stage barriers need the synchronised tile fetch)
     }
 
