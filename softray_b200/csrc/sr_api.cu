@@ -32,6 +32,7 @@ cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstan
                           uint32_t* d_pixels, int32_t* d_ids, unsigned int* d_tile_counter, DevCounters* d_counters,
                           int grid_blocks, cudaStream_t stream);
 int render_kernel_occupancy(int smem_bytes);
+int render_kernel_block_threads();
 cudaError_t measure_fma_peak(bool fp64, int sm_count, cudaStream_t stream, double* tflops);
 cudaError_t build_mesh_on_device(const double* h_verts, int32_t n_verts, const int32_t* h_vidx, const uint32_t* h_argb, int32_t n_tris,
                                  const double bmin[3], const double bmax[3], float pad, int leaf_max, cudaStream_t stream, TriRec** out_tris,
@@ -849,7 +850,7 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
         long long prims = scene->dev.n_spheres;
         for (int32_t t : scene->mesh_tris) prims += t;
         const long long tiles = (long long)((f.width + 7) / 8) * ((rows + 3) / 4) / (f.band_count > 0 ? f.band_count : 1);
-        const bool small_scene = prims <= kPhaseSyncMaxPrims && tiles >= 2LL * ctx->sm_count * (768 / 32);
+        const bool small_scene = prims <= kPhaseSyncMaxPrims && tiles >= 2LL * ctx->sm_count * (768 / 32);      // 768 resident threads per SM
         // (a composite frame can only have bit 0: tile fetch + start of a camera ray, both outside its hierarchy walk)
         f.phase_sync = fr->n_instances == 1 ? env_int("SOFTRAY_PHASE_SYNC", small_scene ? kPhaseSyncStages : 0)
                                             : (env_int("SOFTRAY_PHASE_SYNC", kPhaseSyncComposite) & 1);
@@ -926,7 +927,8 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     { const int cap = env_int("SOFTRAY_BLOCKS_PER_SM", 0); if (cap > 0 && cap < occ) occ = cap; }   // experiments
     const long long n_tiles = (long long)f.tiles_x * f.tiles_y;
     long long grid = (long long)ctx->sm_count * occ;
-    const long long need = (n_tiles + 3) / 4;            // 4 warps per block
+    const int warps_per_block = render_kernel_block_threads() / 32;
+    const long long need = (n_tiles + warps_per_block - 1) / warps_per_block;     // one tile per warp at a time
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     p->grid = (int)grid;

@@ -1632,6 +1632,8 @@ cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstan
     return cudaGetLastError();
 }
 
+int render_kernel_block_threads() { return SR_THREADS; }
+
 int render_kernel_occupancy(int smem_bytes)
 {
     int nb = 0;
