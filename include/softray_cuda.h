@@ -47,6 +47,7 @@ extern "C" {
                                               (voxels, light fields, AO, path tracing, static
                                               shadow cache: they stay on the managed path)          */
 #define SOFTRAY_E_FORMAT             (-7)  /* FormatException from the 3DS loader (Model.cs:555)     */
+#define SOFTRAY_E_TIMEOUT            (-8)  /* softray_host_barrier: a rank process never arrived     */
 
 typedef struct softray_ctx   softray_ctx;    /* opaque: one CUDA device, its streams and buffers     */
 typedef struct softray_scene softray_scene;  /* opaque: device-resident SoA geometry + BVHs          */
@@ -243,7 +244,9 @@ int  softray_host_register(softray_ctx* ctx, void* host_ptr, uint64_t n_bytes);
 int  softray_host_unregister(softray_ctx* ctx, void* host_ptr);
 /* End-of-frame rendezvous of the rank processes that share a host surface: a sense-reversing spin barrier on two
  * uint32 words (zero-initialised by their owner) in memory all of them map.  Returns when n_ranks callers arrived;
- * no CUDA involved (the rank's own softray_render has already returned, i.e. its bands are in host memory). */
+ * no CUDA involved (the rank's own softray_render has already returned, i.e. its bands are in host memory).
+ * A rank that never arrives (crashed) makes the others give up with SOFTRAY_E_TIMEOUT after 60 s
+ * (SOFTRAY_BARRIER_TIMEOUT_S); the words are then unusable. */
 int  softray_host_barrier(volatile uint32_t* two_words, uint32_t n_ranks);
 
 /* ---- diagnostics ------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ E_CUDA = -4
 E_OOM = -5
 E_UNSUPPORTED = -6
 E_FORMAT = -7
+E_TIMEOUT = -8
 
 ACCEL_BVH = 0
 ACCEL_BRUTE = 1
@@ -33,6 +34,7 @@ ERROR_NAMES = {
     E_OOM: "SOFTRAY_E_OOM",
     E_UNSUPPORTED: "SOFTRAY_E_UNSUPPORTED",
     E_FORMAT: "SOFTRAY_E_FORMAT",
+    E_TIMEOUT: "SOFTRAY_E_TIMEOUT",
 }
 
 c_double_p = C.POINTER(C.c_double)

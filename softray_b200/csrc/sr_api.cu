@@ -1143,11 +1143,17 @@ extern "C" int softray_host_barrier(volatile uint32_t* w, uint32_t n_ranks)
         __atomic_add_fetch(generation, 1u, __ATOMIC_RELEASE);
     } else {
         unsigned long long spins = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        const double limit_s = (double)env_int("SOFTRAY_BARRIER_TIMEOUT_S", 60);
         while (__atomic_load_n(generation, __ATOMIC_ACQUIRE) == gen) {
 #if defined(__x86_64__) || defined(__i386__)
             __builtin_ia32_pause();
 #endif
-            if ((++spins & 0xfffff) == 0) std::this_thread::yield();     // a rank that lost its core must not starve the others
+            if ((++spins & 0xfffff) == 0) {
+                std::this_thread::yield();                               // a rank that lost its core must not starve the others
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s)
+                    return fail(nullptr, SOFTRAY_E_TIMEOUT, "softray_host_barrier: a rank did not arrive");
+            }
         }
     }
     return SOFTRAY_OK;

@@ -162,7 +162,7 @@ class SharedHostFramebuffer:
 
         rc = lib.load().softray_host_barrier(self._words.ctypes.data, self.world)
         if rc != 0:
-            raise RuntimeError("softray_host_barrier failed")
+            raise lib.SoftRayError(rc, "softray_host_barrier")
 
     def close(self):
         import torch.distributed as dist

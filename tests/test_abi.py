@@ -110,3 +110,19 @@ def test_synthetic_scenes_are_deterministic_and_valid():
     us = synth.uv_sphere()
     assert us.n_tris == 100_000 and np.isclose(np.abs(us.verts).max(), 0.5)
     assert len(synth.instance_grid()) == 100
+
+
+def test_host_barrier_single_rank_and_timeout(L, monkeypatch):
+    """softray_host_barrier: with one rank it returns at once (any number of generations); a rank that waits for
+    one that never arrives gives up with SOFTRAY_E_TIMEOUT instead of spinning for ever."""
+    import time
+
+    words = np.zeros(2, dtype=np.uint32)
+    for _ in range(5):
+        assert L.softray_host_barrier(words.ctypes.data, 1) == abi.OK
+    assert words[0] == 0 and words[1] == 5
+    monkeypatch.setenv("SOFTRAY_BARRIER_TIMEOUT_S", "1")
+    t = time.perf_counter()
+    assert L.softray_host_barrier(words.ctypes.data, 2) == abi.E_TIMEOUT
+    assert 0.9 < time.perf_counter() - t < 10.0
+    assert L.softray_host_barrier(None, 2) == abi.E_INVALID_ARG
