@@ -118,9 +118,7 @@ __device__ __forceinline__ uint32_t mirror_blend(uint32_t local, uint32_t refl)
 
 struct Counters {
     unsigned int node_visits, prim_tests, sphere_tests, shaded, filter_tests, filter_unsure, filter_mismatch, bundled;
-    // shadow-bundle back-off of this lane: after a failed cone walk the next (2^streak - 1) shading points
-    // do not try one (neighbouring shading points mostly fail alike); a success resets it
-    int bundle_skip, bundle_streak;
+    int bundle_skip;     // shading points this thread has seen (its periodic cone-walk probe, shade_and_shadow)
     int* stack;          // the thread's one traversal stack (kStackEntries), shared by every BVH walk
 };
 // Counters of the out-of-line (exact / per-camera-ray) functions.  These are reached through a pointer,
@@ -1281,7 +1279,7 @@ __device__ __forceinline__ bool occluded_exact(const DevScene& sc, const DevInst
 
 __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const DevScene& sc, const DevInstance& in,
                                                      const DevMesh& m, const double* __restrict__ offsets, const Hit& h,
-                                                     Counters* c, XCounters* xc, unsigned int* n_shadow)
+                                                     Counters* c, XCounters* xc, unsigned int* n_shadow, unsigned int* bundle_score)
 {
     uint32_t color = h.color;
     c->shaded++;
@@ -1297,12 +1295,18 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
         const d3 light = mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]);
         bool all_clear = false;
         if (use_filter && f.point_lighting && !in.sph_can_shadow && f.bundle_budget > 0) {
-            if (c->bundle_skip > 0) {
-                c->bundle_skip--;
-            } else {
+            // Whether cone walks pay is a property of the frame (config2: every one succeeds; config3: none does), and
+            // a thread shades too few points to find out by itself (40 per thread on a 4K frame: a per-thread
+            // exponential back-off still tried at 14 % of config3's shading points, 45.5 vs 43.0 ms without).  The
+            // block keeps the score: its first 64 attempts explore, then a point tries only while at least one attempt
+            // in 32 succeeds (a success saves ~100 rays, a failure costs two or three), plus one probe per 256 points
+            // of a thread so that a block can change its mind.
+            const unsigned int ok = bundle_score[0], bad = bundle_score[1];
+            c->bundle_skip++;                                      // (shading points of this thread)
+            if (bad < 64u || ok * 32u >= bad || (c->bundle_skip & 255) == 0) {
                 all_clear = bundle_clear(m, end, light, f.light_radius, f.bundle_budget, c);
-                if (all_clear) { c->bundled += (unsigned int)n; c->bundle_streak = 0; }
-                else { c->bundle_streak = min(c->bundle_streak + 1, 6); c->bundle_skip = (1 << c->bundle_streak) - 1; }
+                if (all_clear) c->bundled += (unsigned int)n;
+                atomicAdd(&bundle_score[all_clear ? 0 : 1], 1u);
             }
         }
         if (all_clear && f.filter_mode != 2) escaped = n;
@@ -1367,7 +1371,7 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
 __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const DevScene& sc, const DevInstance* __restrict__ insts,
                                                      const double* __restrict__ offsets, const d3* starts, const d3* dirs_view_or_world,
                                                      bool dirs_are_view, Counters* c, XCounters* xc, unsigned int* n_shadow,
-                                                     unsigned int* n_secondary, bool* hit_out, int sync, bool valid)
+                                                     unsigned int* n_secondary, bool* hit_out, int sync, bool valid, unsigned int* bundle_score)
 {
     PixelOut out; out.color = f.background; out.id = -1;
     Hit h; int which = 0; bool hit = false;
@@ -1453,7 +1457,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
     const int bounces = (f.reflection_depth > 0 && f.n_instances == 1) ? f.reflection_depth : 0;
     d3 d = dir0;
     for (int b = 0;; b++) {
-        local[depth] = shade_and_shadow(f, sc, in, m, offsets, h, c, xc, n_shadow);
+        local[depth] = shade_and_shadow(f, sc, in, m, offsets, h, c, xc, n_shadow, bundle_score);
         if (b >= bounces) break;
         // r = d - n * (2 (d.n)), from pos + n*0.001 (PathTracingMethod.cs:10,52)
         const d3 r = vsub(d, vscale(h.normal, dmul(2.0, vdot(d, h.normal))));
@@ -1498,7 +1502,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     const int n_tiles = f.tiles_x * f.tiles_y;
     Counters c; c.node_visits = 0; c.prim_tests = 0; c.sphere_tests = 0; c.shaded = 0;
     c.filter_tests = 0; c.filter_unsure = 0; c.filter_mismatch = 0; c.bundled = 0;
-    c.bundle_skip = 0; c.bundle_streak = 0;
+    c.bundle_skip = 0;
     int walk_stack[kStackEntries];
     c.stack = walk_stack;
     XCounters xc; xc.stack = walk_stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0; xc.filter_unsure = 0;
@@ -1509,6 +1513,9 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     // together.  Every warp takes part in every barrier: one without a tile repeats the last tile and discards the
     // result (into xc_void).
     __shared__ int s_tile_base;
+    __shared__ unsigned int s_bundle_score[2];      // cone walks of this block that succeeded / failed (shade_and_shadow)
+    if (threadIdx.x == 0) { s_bundle_score[0] = 0u; s_bundle_score[1] = 0u; }
+    __syncthreads();
     const int sync = f.phase_sync;             // bit 0: tile fetch + start of a camera ray; bits 1-4: the stages of closest_hit
     XCounters xc_void = xc;
     for (;;) {
@@ -1575,7 +1582,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
             if (valid) n_primary++;
             bool hit = false;
             const PixelOut s1 = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, valid ? &xc : &xc_void, &n_shadow,
-                                                 &n_secondary, &hit, sync, valid);
+                                                 &n_secondary, &hit, sync, valid, s_bundle_score);
             if (!valid) continue;
             if (hit) n_hits++;
             int* pa = s_acc[threadIdx.x >> 5][px];

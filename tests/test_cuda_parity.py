@@ -513,7 +513,7 @@ def test_handles_may_be_released_in_any_order(lib, obj_mesh):
 
 def test_phase_sync_changes_nothing(lib, ctx, obj_mesh, monkeypatch):
     """Stage barriers (sr_render.cu "Phase synchronisation") only change WHEN warps run what: frames, hit ids and
-    every counter must be identical with them forced on and off -- including frames whose tiles do not fill the
+    the ray counters must be identical with them forced on and off -- including frames whose tiles do not fill the
     last block (warps without a tile), widths / heights that are not multiples of the 8x4 tile (lanes without a
     pixel), supersampling, focal blur, shadows, mirror bounces and spheres."""
     meshes2, spheres2, p2 = synth.config2(width=203, height=117, shadow_samples=16, n_spheres=300)
@@ -531,7 +531,8 @@ def test_phase_sync_changes_nothing(lib, ctx, obj_mesh, monkeypatch):
             out[mode] = sc.render(p, want_ids=True)
         a, b = out["0"], out["1"]
         assert np.array_equal(a["pixels"], b["pixels"]) and np.array_equal(a["ids"], b["ids"])
-        for k in ("rays_primary", "rays_shadow", "rays_secondary", "hits_primary", "shaded_hits", "node_visits", "prim_tests",
-                  "sphere_tests", "filter_tests", "filter_unsure", "rays_bundled"):
+        # (which shading points try a cone walk depends on their block's running score, i.e. on timing: the search
+        # counters may differ between any two runs, the rays and what they hit may not)
+        for k in ("rays_primary", "rays_shadow", "rays_secondary", "hits_primary", "shaded_hits"):
             assert getattr(a["stats"], k) == getattr(b["stats"], k), k
         sc.close()
