@@ -26,6 +26,7 @@
 #include "../../include/softray_cuda.h"
 #include "sr_bvh.h"
 #include "sr_types.h"
+#include "sr_wave.h"
 
 namespace sr {
 cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets,
@@ -53,6 +54,11 @@ struct softray_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_staged = nullptr;   // the last frame's constants have left the pinned staging
     bool staging_busy = false;
+    // every frame of a context shares d_insts / d_tile_counter / d_counters: a frame enqueued on another stream
+    // than the previous one first waits for that one's kernel (softray_render_device is asynchronous)
+    cudaEvent_t ev_frame = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_last_frame = false;
     // per-frame device scratch (sized for SOFTRAY_MAX_INSTANCES / SOFTRAY_MAX_SHADOW_SAMPLES)
     DevInstance* d_insts = nullptr;
     double* d_offsets = nullptr;
@@ -72,6 +78,13 @@ struct softray_ctx {
     int32_t* d_ids = nullptr;
     size_t fb_capacity = 0, ids_capacity = 0;
     int cached_seed = 0, cached_samples = -1;   // area-light offsets currently in h_offsets
+    // stage-kernel pipeline (sr_wave.cu): one arena for the records that cross HBM between the stages, grown on demand
+    void* wave_base = nullptr;
+    size_t wave_bytes = 0;
+    uint32_t wave_cap = 0;                      // samples per chunk the arena is laid out for
+    int wave_slots = 0;                         // shading points per sample (1 + bounces)
+    int last_launches = 1;                      // kernels the last frame launched (softray_stats.launches)
+    WaveBufs wave;
     std::string err;
 };
 
@@ -426,11 +439,12 @@ extern "C" void softray_destroy(softray_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_insts); cudaFree(ctx->d_offsets); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_pixels); cudaFree(ctx->d_ids);
+    cudaFree(ctx->d_pixels); cudaFree(ctx->d_ids); cudaFree(ctx->wave_base);
     cudaFreeHost(ctx->h_insts); cudaFreeHost(ctx->h_offsets); cudaFreeHost(ctx->h_counters);
     cudaFree(ctx->d_tlas_nodes); cudaFree(ctx->d_tlas_order); cudaFreeHost(ctx->h_tlas_nodes); cudaFreeHost(ctx->h_tlas_order);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
+    if (ctx->ev_frame) cudaEventDestroy(ctx->ev_frame);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -456,6 +470,7 @@ extern "C" int softray_create(int32_t device_ordinal, softray_ctx** out)
         SR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         for (auto& ev : ctx->ev) SR_CUDA(ctx, cudaEventCreate(&ev));
         SR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming));
+        SR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_frame, cudaEventDisableTiming));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_insts, sizeof(DevInstance) * SOFTRAY_MAX_INSTANCES));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_offsets, sizeof(double) * 3 * SOFTRAY_MAX_SHADOW_SAMPLES));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_tile_counter, sizeof(unsigned int)));
@@ -740,6 +755,8 @@ struct Prepared {
     int grid = 0;
     size_t smem = 0;
     int start_row = 0, end_row = -1;
+    bool wave = false;                 // stage kernels (sr_wave.cu) instead of the fused kernel
+    bool empty = false;                // no row to trace (start_row > end_row after the clamp): nothing is launched
 };
 
 // A sphere reports rayFrac = distance from the ray start to the hit point (Sphere.cs:160,197) and a
@@ -807,6 +824,9 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     int e = fr->end_row < 0 ? 0 : fr->end_row;     if (e > fr->height - 1) e = fr->height - 1;
     f.start_row = s; f.end_row = e;
     p->start_row = s; p->end_row = e;
+    // start_row > end_row after the clamp: the reference's row loop (Renderer.cs:1659-1670) runs zero times
+    p->empty = e < s;
+    if (p->empty) { f.tiles_x = 0; f.tiles_y = 0; p->grid = 0; return SOFTRAY_OK; }
     f.sub_pixel_res = fr->sub_pixel_res;
     f.focal_blur = fr->focal_blur ? 1 : 0;
     f.subdivision = fr->subdivision ? 1 : 0;
@@ -932,6 +952,22 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     p->grid = (int)grid;
+
+    // Which pipeline.  The stage kernels cover what the big frames use: library-built trees, the filtered search,
+    // meshes only.  Small cache-resident scenes stay on the fused kernel (one launch, stage barriers); everything the
+    // stage kernels do not implement (spheres, brute force, FILTER_OFF / _VERIFY) does too.  SOFTRAY_PIPELINE=fused|wave
+    // overrides the size rule, never the capability rule.
+    {
+        long long prims = scene->dev.n_spheres;
+        for (int32_t t : scene->mesh_tris) prims += t;
+        const bool capable = scene->dev.accel != SOFTRAY_ACCEL_BRUTE && f.filter_mode == SOFTRAY_FILTER_AUTO && scene->dev.n_spheres == 0 &&
+                             scene->dev.n_meshes > 0;
+        const char* e = std::getenv("SOFTRAY_PIPELINE");
+        bool want = prims > kPhaseSyncMaxPrims || fr->n_instances > 1;
+        if (e && !std::strcmp(e, "fused")) want = false;
+        if (e && !std::strcmp(e, "wave")) want = true;
+        p->wave = capable && want;
+    }
     return SOFTRAY_OK;
 }
 
@@ -949,6 +985,7 @@ int enqueue_frame(softray_ctx* ctx, const softray_scene* scene, const Prepared& 
                   cudaStream_t stream, bool timed)
 {
     const DevFrame& f = p.f;
+    if (ctx->have_last_frame && ctx->last_stream != stream) SR_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_frame, 0));
     if (timed) SR_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
     SR_CUDA(ctx, cudaMemcpyAsync(ctx->d_insts, ctx->h_insts, sizeof(DevInstance) * (size_t)f.n_instances,
                                  cudaMemcpyHostToDevice, stream));
@@ -966,9 +1003,38 @@ int enqueue_frame(softray_ctx* ctx, const softray_scene* scene, const Prepared& 
     SR_CUDA(ctx, cudaMemsetAsync(ctx->d_tile_counter, 0, sizeof(unsigned int), stream));
     SR_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(DevCounters), stream));
     if (timed) SR_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
+    ctx->last_launches = 1;
+    if (p.wave) {
+        const int nn = f.sub_pixel_res * f.sub_pixel_res;
+        const int slots = 1 + ((f.reflection_depth > 0 && f.n_instances == 1) ? f.reflection_depth : 0);
+        const long long frame_samples = (long long)f.tiles_x * f.tiles_y * 32 * nn;
+        long long cap = env_int("SOFTRAY_WAVE_CHUNK", 1 << 23);
+        if (cap > frame_samples) cap = frame_samples;
+        if (cap < 32LL * nn) cap = 32LL * nn;
+        cap = cap / (32LL * nn) * (32LL * nn);
+        if (ctx->wave_cap < (uint32_t)cap || ctx->wave_slots < slots) {
+            // (grow only: frames of one host keep their size; a bigger frame reallocates once)
+            SR_CUDA(ctx, cudaStreamSynchronize(stream));
+            if (ctx->stream != stream) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->wave_base); ctx->wave_base = nullptr; ctx->wave_cap = 0; ctx->wave_bytes = 0;
+            const uint32_t new_cap = (uint32_t)std::max<long long>(cap, ctx->wave_cap);
+            const int new_slots = std::max(slots, ctx->wave_slots);
+            WaveLayout lay;
+            const size_t bytes = wave_buffer_bytes(new_cap, new_slots, &lay);
+            SR_CUDA(ctx, cudaMalloc(&ctx->wave_base, bytes));
+            wave_bind(ctx->wave_base, lay, &ctx->wave);
+            ctx->wave_bytes = bytes; ctx->wave_cap = new_cap; ctx->wave_slots = new_slots;
+        }
+        int launches = 0;
+        SR_CUDA(ctx, wave_render(f, scene->dev, ctx->d_insts, ctx->d_offsets, ctx->wave, (uint32_t)cap, d_pixels, d_ids, ctx->d_counters,
+                                 ctx->sm_count, stream, &launches));
+        ctx->last_launches = launches;
+    } else
     SR_CUDA(ctx, launch_render(f, scene->dev, ctx->d_insts, ctx->d_offsets, d_pixels, d_ids, ctx->d_tile_counter,
                                ctx->d_counters, p.grid, stream));
     if (timed) SR_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
+    SR_CUDA(ctx, cudaEventRecord(ctx->ev_frame, stream));
+    ctx->last_stream = stream; ctx->have_last_frame = true;
     return SOFTRAY_OK;
 }
 
@@ -983,7 +1049,7 @@ int collect_stats(softray_ctx* ctx, cudaStream_t stream, softray_stats* st, bool
     st->hits_primary = c.hits_primary; st->shaded_hits = c.shaded_hits;
     st->filter_tests = c.filter_tests; st->filter_unsure = c.filter_unsure; st->filter_mismatch = c.filter_mismatch;
     st->rays_bundled = c.rays_bundled;
-    st->launches = 1;
+    st->launches = (uint64_t)ctx->last_launches;
     float ms = 0.f;
     SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); st->ms_h2d = ms;
     SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); st->ms_kernel = ms;
@@ -1004,7 +1070,10 @@ extern "C" int softray_render_device(softray_ctx* ctx, const softray_scene* scen
     Prepared p;
     int rc = prepare_frame(ctx, scene, frame, &p);
     if (rc != SOFTRAY_OK) return rc;
-    if (p.f.tiles_y == 0) return SOFTRAY_OK;
+    if (p.empty || p.f.tiles_y == 0) {          // no row of the frame is ours: nothing to launch, all counters zero
+        if (stats) std::memset(stats, 0, sizeof *stats);
+        return SOFTRAY_OK;
+    }
     rc = enqueue_frame(ctx, scene, p, d_pixels_argb, d_hit_ids, s, stats != nullptr);
     if (rc != SOFTRAY_OK) return rc;
     if (stats) {
@@ -1025,6 +1094,10 @@ extern "C" int softray_render(softray_ctx* ctx, const softray_scene* scene, cons
     Prepared p;
     int rc = prepare_frame(ctx, scene, frame, &p);
     if (rc != SOFTRAY_OK) return rc;
+    if (p.empty || p.f.tiles_y == 0) {
+        if (stats) std::memset(stats, 0, sizeof *stats);
+        return SOFTRAY_OK;
+    }
     const size_t n_px = (size_t)frame->width * (size_t)frame->height;
     // A page-locked (CUDA-registered / cudaHostAlloc'd) caller buffer is mapped into the device's address
     // space: the kernel then stores finished pixels straight into it over PCIe, overlapped with tracing,

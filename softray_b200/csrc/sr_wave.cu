@@ -1,0 +1,736 @@
+// sr_wave.cu -- the raytrace hot path as STAGE KERNELS (DESIGN.md "Stage kernels"): the same per-ray arithmetic
+// as the fused kernel (sr_render.cu; both include sr_device.cuh), cut where the fused kernel's own profile says it
+// hurts -- a 38.8 K-instruction program against a 32 KB instruction cache, 80 registers per thread (37 % occupancy)
+// under latency-bound walks, half the lanes idle because the rays of a warp need different stages at different
+// times, and a frame whose slowest tile holds an SM while the others idle.
+//
+// One frame = chunks of 8x4-pixel tiles; per chunk (records cross HBM between the stages):
+//   search<CAMERA>   ray generation (exact FP64) + FP32 filtered closest-hit walk (instance hierarchy for composite
+//                    frames)                                   -> <= 4 candidate triangles per sample (Cand, 20 B)
+//   hit<CAMERA>      the candidates through the reference arithmetic (root-box clip + Triangle.IntersectRay) ->
+//                    winner; Texture3D + ShadingMethod        -> slot colour (4 B), shadow work item (32 B),
+//                                                                 reflection ray (56 B); undecided rays -> a list
+//   fallback<CAMERA> the full exact walk for the few rays the search could not bracket (compacted: whole warps of them)
+//   search/hit/fallback<LIST>   the same for the reflection rays, once per bounce
+//   shadow           ShadowMethod.TraceRaysForSoftShadows over the compacted shading points: cone test, then the
+//                    filtered any-hit rays; undecided rays -> a list      -> escaped count per slot
+//   shadow_fallback  those rays through the reference arithmetic
+//   compose          ModulatePackedColor by the shadow byte, mirror blend chain, sub-pixel sums, packed-ARGB store
+// Every stage keeps the fused kernel's arithmetic, so frames are identical bit for bit (tests/test_cuda_wave.py
+// requires wave == fused == oracle).  Replaces RaytraceBlock -> TraceRayComplex -> IRayIntersectable.IntersectRay ->
+// Surface.DrawPixel (Engine3D/Renderer.cs:1690-1925 and the Raytrace/*Method.cs decorators), like sr_render.cu.
+#include "sr_device.cuh"
+#include "sr_wave.h"
+
+namespace sr {
+
+namespace {
+
+constexpr int kWaveThreads = 256;
+
+enum : uint32_t { kStateInvalid = 0, kStateMiss = 1, kStateListed = 2, kStateUndecided = 3 };
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// Append one record per lane with `want` to a device queue: one atomic per warp.  Must be reached by all 32 lanes.
+__device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool want)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    uint32_t base = 0;
+    if (mask != 0u && lane_id() == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, mask ? __ffs(mask) - 1 : 0);
+    return base + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u));
+}
+
+__device__ __forceinline__ void flush_counters(DevCounters* counters, const unsigned long long (&v)[12])
+{
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane_id() == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + k, x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rays of a batch
+// ---------------------------------------------------------------------------------------------
+// RaytraceBlock's ray generation (Renderer.cs:1717-1797) for work item w of a tile: the same operations as the
+// fused kernel's loop body.  Returns false for items outside the image / band.
+__device__ __forceinline__ bool camera_ray(const DevFrame& f, const DevInstance& in0, int tile, int w, d3* start, d3* dir, bool* is_view)
+{
+    const int n = f.sub_pixel_res, nn = n * n;
+    const int W = f.width, H = f.height;
+    const int ty = tile / f.tiles_x, tx = tile - ty * f.tiles_x;
+    const int band_j = ty / f.tiles_per_band;
+    const int row0 = f.start_row + (f.band_index + band_j * f.band_count) * f.band_height;
+    const int band_r0 = (ty - band_j * f.tiles_per_band) * 4;
+    const int px = w / nn, si = w - px * nn;
+    const int col = tx * 8 + (px & 7);
+    const int band_r = band_r0 + (px >> 3);
+    const int row = row0 + band_r;
+    if (col >= W || band_r >= f.band_height || row > f.end_row) return false;
+    const int sx = si / n, sy = si - sx * n;                                      // subX outer, subY inner (:1762-1764)
+    double fx = 0.0, fy = 0.0;
+    if (n > 1) {
+        fx = dsub(ddiv((double)sx, (double)(n - 1)), 0.5);                        // :1767-1768
+        fy = dsub(ddiv((double)sy, (double)(n - 1)), 0.5);
+    }
+    if (f.focal_blur && n > 1) {                                                  // App. A #11
+        const d3 dir_view = mk(-dsub(ddiv((double)col, (double)W), 0.5), dmul(-dsub(ddiv((double)row, (double)H), 0.5), f.aspect),
+                               f.fov_depth);
+        const d3 dw = mul3x3(in0.Minv, dir_view);
+        const d3 focal_pt = vadd(vscale(dw, f.focal_depth), mk(in0.start[0], in0.start[1], in0.start[2]));   // :1759
+        const d3 sv = mk(dmul(ddiv(fx, (double)W), f.focal_strength), dmul(ddiv(fy, (double)H), f.focal_strength), -in0.pos_z);
+        *start = mul3x3(in0.Minv, sv);                                            // :1776-1778
+        *dir = vsub(focal_pt, *start);                                            // :1790
+        *is_view = false;
+    } else {
+        *start = mk(in0.start[0], in0.start[1], in0.start[2]);
+        *dir = mk(-dsub(ddiv(dadd((double)col, fx), (double)W), 0.5), dmul(-dsub(ddiv(dadd((double)row, fy), (double)H), 0.5), f.aspect),
+                  f.fov_depth);                                                   // :1728, :1794-1796
+        *is_view = true;
+    }
+    return true;
+}
+
+// SRC 0: camera rays of the chunk (ray r = sample r); SRC 1: the reflection rays of list `a.ref_in`.
+// For a single-instance frame *dir is in model space; for a composite frame it stays in view space (every instance
+// rotates it for itself).
+template <int SRC>
+__device__ __forceinline__ bool batch_ray(const WaveArgs& a, const DevInstance* __restrict__ insts, uint32_t r, d3* start, d3* dir,
+                                          uint32_t* sample, uint32_t* depth)
+{
+    const DevFrame& f = a.f;
+    if (SRC == 0) {
+        const int nn = f.sub_pixel_res * f.sub_pixel_res;
+        const int per_tile = 32 * nn;
+        const int t = (int)(r / (uint32_t)per_tile), w = (int)(r - (uint32_t)t * (uint32_t)per_tile);
+        bool is_view;
+        *sample = r; *depth = 0;
+        if (!camera_ray(f, insts[0], a.tile0 + t, w, start, dir, &is_view)) return false;
+        if (f.n_instances == 1 && is_view) *dir = mul3x3(insts[0].Minv, *dir);
+        return true;
+    } else {
+        const RefRay* q = a.b.ref[a.ref_in] + r;
+        const double2 v0 = ldg2(q, 0), v1 = ldg2(q, 1), v2 = ldg2(q, 2);
+        *start = mk(v0.x, v0.y, v1.x);
+        *dir = mk(v1.y, v2.x, v2.y);
+        const uint2 sd = __ldg(reinterpret_cast<const uint2*>(q) + 6);
+        *sample = sd.x; *depth = sd.y;
+        return true;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// search: candidates of one ray
+// ---------------------------------------------------------------------------------------------
+struct Search {
+    float best_hi;                 // upper bound (ray-parameter units) of the nearest SURE hit so far
+    int n;                         // candidates listed (> kMaxCand: too many)
+    int k[kMaxCand];
+    int inst[kMaxCand];
+    float lo[kMaxCand];            // lower bound of each candidate's rayFrac
+    bool undecided;
+};
+
+__device__ __forceinline__ void search_add(Search& st, int inst, int k, float lo)
+{
+    if (st.n >= kMaxCand) {
+        // drop what a nearer sure hit has already beaten, then try again
+        int m = 0;
+#pragma unroll
+        for (int j = 0; j < kMaxCand; j++)
+            if (st.lo[j] <= st.best_hi) { st.k[m] = st.k[j]; st.inst[m] = st.inst[j]; st.lo[m] = st.lo[j]; m++; }
+        st.n = m;
+        if (m >= kMaxCand) { st.n = kMaxCand + 1; return; }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxCand; j++)
+        if (j == st.n) { st.k[j] = k; st.inst[j] = inst; st.lo[j] = lo; }
+    st.n++;
+}
+
+// The mesh of one instance against one ray (model space): merges its candidates into st.  Same walk as the
+// fused kernel's closest_hit (fray_setup_fwd + walk_filter_closest); rayFrac = t0 + tau.
+__device__ __forceinline__ void search_mesh(const DevMesh& m, int subdivision, d3 s, d3 dir, int inst, Search& st, XCounters* c)
+{
+    if (m.n_tris <= 0) return;
+    FRay r; double t0;
+    const int known = fray_setup_fwd(m, subdivision, s, dir, &r, &t0);
+    if (known == 0) return;
+    if (known == 2) { st.undecided = true; return; }
+    const float limit_tau = st.best_hi < 1e29f ? __double2float_ru((double)st.best_hi - t0) * (1.0f + 4.0f * kU) + 1e-6f : 1e30f;
+    if (limit_tau < 0.0f) return;                       // the whole mesh lies behind a sure hit of another instance
+    FClosest fc;
+    walk_filter_closest(m.nodes, m.filt, m.n_tris, r, m.scale, &fc, c, limit_tau);
+    if (fc.n_cand == 0) return;
+    if (fc.n_cand > kMaxCand) { st.undecided = true; return; }
+    if (fc.best_k >= 0) {
+        const float hi = __double2float_ru(t0 + (double)fc.best_hi) * (1.0f + 2.0f * kU);
+        if (hi < st.best_hi) st.best_hi = hi;
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxCand; j++) {
+        if (j < fc.n_cand && (fc.cand[j] == fc.best_k || fc.cand_lo[j] <= fc.best_hi)) {
+            const float lo = __double2float_rd(t0 + (double)fc.cand_lo[j]) * (1.0f - 2.0f * kU);
+            if (st.n <= kMaxCand) search_add(st, inst, fc.cand[j], lo);
+        }
+    }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(kWaveThreads) k_search(const __grid_constant__ WaveArgs a)
+{
+    const DevFrame& f = a.f;
+    const DevInstance* __restrict__ insts = a.insts;
+    int walk_stack[kStackEntries];
+    XCounters xc; xc.stack = walk_stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0;
+    xc.filter_unsure = 0; xc.filter_mismatch = 0;
+    const uint32_t n_rays = SRC == 0 ? a.n_rays : __ldg(&a.b.counts->n_ref[a.ref_in]);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_rays; base += stride) {
+        const uint32_t r = base + lane_id();
+        if (r >= n_rays) continue;
+        d3 s, dir; uint32_t sample, depth;
+        if (!batch_ray<SRC>(a, insts, r, &s, &dir, &sample, &depth)) { a.b.meta[r] = kStateInvalid; continue; }
+        Search st; st.best_hi = 1e30f; st.n = 0; st.undecided = false;
+#pragma unroll
+        for (int j = 0; j < kMaxCand; j++) { st.k[j] = -1; st.inst[j] = 0; st.lo[j] = 0.0f; }
+        if (f.n_instances == 1) {
+            search_mesh(a.sc.meshes[insts[0].mesh], f.subdivision, s, dir, 0, st, &xc);
+        } else {
+            // composite frame: the hierarchy over the view-space boxes of the instances, front to
+            // back; rigid transforms keep |dir|, so every instance's rayFrac is the parameter along the view ray
+            FRay tr;
+            tr.ox = tr.oy = tr.oz = 0.0f;
+            tr.gx = __double2float_rn(dir.x); tr.gy = __double2float_rn(dir.y); tr.gz = __double2float_rn(dir.z);
+            tr.ix = __fdiv_rn(1.0f, tr.gx); tr.iy = __fdiv_rn(1.0f, tr.gy); tr.iz = __fdiv_rn(1.0f, tr.gz);
+            tr.nox = tr.noy = tr.noz = 0.0f;
+            tr.tcull = CUDART_INF_F;
+            int stack[kTlasStackEntries];
+            int sp = 0, cur = 0;
+            for (;;) {
+                if (cur >= 0) {
+                    const float4* p = reinterpret_cast<const float4*>(f.tlas_nodes + cur);
+                    const float4 A = __ldg(p), B = __ldg(p + 1), CC = __ldg(p + 2);
+                    const int4 d = __ldg(reinterpret_cast<const int4*>(p + 3));
+                    xc.node_visits++;
+                    float t0, t1;
+                    const bool h0 = fslab(tr, A.x, A.y, A.z, A.w, B.x, B.y, &t0);
+                    const bool h1 = fslab(tr, B.z, B.w, CC.x, CC.y, CC.z, CC.w, &t1);
+                    if (h0 && h1) {
+                        const bool first0 = t0 <= t1;
+                        stack[sp++] = first0 ? d.y : d.x;
+                        cur = first0 ? d.x : d.y;
+                        continue;
+                    }
+                    if (h0) { cur = d.x; continue; }
+                    if (h1) { cur = d.y; continue; }
+                } else {
+                    const int code = -1 - cur;
+                    const int first = code >> 4, count = code & 15;
+                    for (int j = 0; j < count; j++) {
+                        const int i = __ldg(f.tlas_order + first + j);
+                        const DevInstance& in = insts[i];
+                        search_mesh(a.sc.meshes[in.mesh], f.subdivision, mk(in.start[0], in.start[1], in.start[2]), mul3x3(in.Minv, dir), i,
+                                    st, &xc);
+                        if (st.best_hi < 1e29f) tr.tcull = st.best_hi * 1.00002f + 1e-6f;
+                    }
+                }
+                if (sp == 0 || st.undecided || st.n > kMaxCand) break;
+                cur = stack[--sp];
+            }
+        }
+        uint32_t state;
+        int4 cand = make_int4(-1, -1, -1, -1);
+        uint32_t insts_of = 0;
+        if (st.undecided || st.n > kMaxCand) state = kStateUndecided;
+        else {
+            int m = 0;
+            int ck[kMaxCand] = {-1, -1, -1, -1};
+#pragma unroll
+            for (int j = 0; j < kMaxCand; j++)
+                if (j < st.n && st.lo[j] <= st.best_hi) {
+#pragma unroll
+                    for (int q = 0; q < kMaxCand; q++)
+                        if (q == m) { ck[q] = st.k[j]; insts_of |= (uint32_t)st.inst[j] << (4 + 7 * q); }
+                    m++;
+                }
+            cand = make_int4(ck[0], ck[1], ck[2], ck[3]);
+            state = m == 0 ? kStateMiss : kStateListed;
+        }
+        a.b.cand[r] = cand;
+        a.b.meta[r] = state | insts_of;
+    }
+    const unsigned long long v[12] = {0, 0, 0, xc.node_visits, 0, 0, 0, 0, xc.filter_tests, 0, 0, 0};
+    flush_counters(a.counters, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// hit: exact winner among the candidates, then Texture3D + ShadingMethod, then the work the hit spawns
+// ---------------------------------------------------------------------------------------------
+struct ExactHit { bool hit; int inst; int k; int index; double rf_from_clip; double rf; d3 clipped_start; d3 dir; };
+
+// What the fused kernel's trace_camera_ray does after closest_hit returned: record the shading point.
+// Returns through the flags what this lane appends to the queues.  All lanes of the warp call it.
+template <int SRC>
+__device__ __forceinline__ void spawn_from_hit(const WaveArgs& a, const DevInstance* __restrict__ insts, bool active, bool hit,
+                                               const ExactHit& eh, uint32_t sample, uint32_t depth, unsigned int* n_shaded,
+                                               unsigned int* n_shadow, unsigned int* n_secondary, unsigned int* n_hits)
+{
+    const DevFrame& f = a.f;
+    const uint32_t S = a.n_samples;
+    bool want_shadow = false, want_ref = false;
+    ShadowItem item; RefRay ray;
+    if (active) {
+        if (!hit) {
+            if (SRC == 0) a.b.sample_state[sample] = 0x80u;                      // valid, no shading point: background
+            else a.b.sample_state[sample] = (uint8_t)(0x80u | 0x08u | depth);    // `depth` shading points, then the background (tail)
+        } else {
+            const DevInstance& in = insts[eh.inst];
+            const DevMesh& m = a.sc.meshes[in.mesh];
+            const TriRec* t = m.tris + eh.k;
+            const double2 a0 = ldg2(t, 0), a1 = ldg2(t, 1);
+            const d3 pos = vadd(eh.clipped_start, vscale(eh.dir, eh.rf_from_clip));   // Plane.cs:86 from the clipped start
+            const d3 normal = mk(a0.x, a0.y, a1.x);
+            uint32_t color = __ldg(reinterpret_cast<const uint32_t*>(t) + 30);
+            if (SRC == 0) { a.b.sample_id[sample] = in.tri_base + eh.index; (*n_hits)++; }
+            (*n_shaded)++;
+            if (f.texture3d_id) color = modulate(color, texture3d_sample(f.texture3d_id, pos));
+            if (f.shading) color = shade(f, in, pos, normal, color);
+            const uint32_t slot = depth * S + sample;
+            a.b.slot_color[slot] = color;
+            a.b.sample_state[sample] = (uint8_t)(0x80u | (depth + 1u));
+            if (f.shadows) {
+                const d3 end = vadd(pos, vscale(normal, 0.001));                  // ShadowMethod.cs:150
+                item.end[0] = end.x; item.end[1] = end.y; item.end[2] = end.z; item.slot = slot; item.inst = (uint32_t)eh.inst;
+                want_shadow = true;
+                *n_shadow += (unsigned int)f.shadow_samples;
+            }
+            const int bounces = (f.reflection_depth > 0 && f.n_instances == 1) ? f.reflection_depth : 0;
+            if ((int)depth < bounces) {
+                // r = d - n * (2 (d.n)), from pos + n*0.001 (PathTracingMethod.cs:10,52)
+                const d3 rd = vsub(eh.dir, vscale(normal, dmul(2.0, vdot(eh.dir, normal))));
+                const d3 rs = vadd(pos, vscale(normal, 0.001));
+                ray.o[0] = rs.x; ray.o[1] = rs.y; ray.o[2] = rs.z; ray.d[0] = rd.x; ray.d[1] = rd.y; ray.d[2] = rd.z;
+                ray.sample = sample; ray.depth = depth + 1u;
+                want_ref = true;
+                (*n_secondary)++;
+            }
+        }
+    }
+    if (f.shadows) {
+        const uint32_t at = warp_append(&a.b.counts->n_shadow, want_shadow);
+        if (want_shadow) a.b.shadow[at] = item;
+    }
+    if (f.reflection_depth > 0 && f.n_instances == 1) {
+        const uint32_t at = warp_append(&a.b.counts->n_ref[a.ref_out], want_ref);
+        if (want_ref) a.b.ref[a.ref_out][at] = ray;
+    }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(kWaveThreads) k_hit(const __grid_constant__ WaveArgs a)
+{
+    const DevFrame& f = a.f;
+    const DevInstance* __restrict__ insts = a.insts;
+    int walk_stack[4];                  // (the listed-candidate evaluators never walk)
+    XCounters xc; xc.stack = walk_stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0;
+    xc.filter_unsure = 0; xc.filter_mismatch = 0;
+    unsigned int n_primary = 0, n_shadow = 0, n_secondary = 0, n_hits = 0, n_shaded = 0;
+    const uint32_t n_rays = SRC == 0 ? a.n_rays : __ldg(&a.b.counts->n_ref[a.ref_in]);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_rays; base += stride) {
+        const uint32_t r = base + lane_id();
+        bool active = r < n_rays;
+        d3 s = mk(0, 0, 0), dir = mk(0, 0, 0); uint32_t sample = 0, depth = 0;
+        uint32_t meta = kStateInvalid;
+        if (active) {
+            meta = a.b.meta[r];
+            active = batch_ray<SRC>(a, insts, r, &s, &dir, &sample, &depth);
+            if (SRC == 0 && !active) a.b.sample_state[r] = 0u;                    // outside the image / band (r < n_rays here)
+        }
+        const uint32_t state = meta & 3u;
+        ExactHit eh; eh.hit = false; eh.inst = 0; eh.k = -1; eh.index = 0x7fffffff; eh.rf = kNoHit; eh.rf_from_clip = 0.0;
+        eh.clipped_start = s; eh.dir = dir;
+        bool undecided = false;
+        if (active) {
+            if (SRC == 0) n_primary++;
+            if (state == kStateUndecided) { undecided = true; xc.filter_unsure++; }
+            else if (state == kStateListed) {
+                const int4 cv = a.b.cand[r];
+                const int ck[kMaxCand] = {cv.x, cv.y, cv.z, cv.w};
+                if (f.n_instances == 1) {
+                    int list[kMaxCand]; int n_list = 0;
+#pragma unroll
+                    for (int j = 0; j < kMaxCand; j++) if (ck[j] >= 0) list[n_list++] = ck[j];
+                    if (n_list > 1) xc.filter_unsure++;
+                    BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
+                    d3 ts; double offset;
+                    if (n_list > 0)     // (always: lets the compiler drop the evaluator's full-walk branch from this kernel)
+                        mesh_closest_exact(a.sc.meshes[insts[0].mesh], f.subdivision, s, dir, list, n_list, &bt, &ts, &offset, &xc);
+                    if (bt.k >= 0) {
+                        eh.hit = true; eh.k = bt.k; eh.index = bt.index; eh.rf_from_clip = bt.rf; eh.rf = dadd(bt.rf, offset);
+                        eh.clipped_start = ts;
+                    }
+                } else {
+                    int n_list = 0;
+#pragma unroll
+                    for (int j = 0; j < kMaxCand; j++) {
+                        if (ck[j] < 0) continue;
+                        n_list++;
+                        const int i = (int)((meta >> (4 + 7 * j)) & 127u);
+                        const DevInstance& in = insts[i];
+                        const d3 si = mk(in.start[0], in.start[1], in.start[2]);
+                        const d3 di = mul3x3(in.Minv, dir);
+                        BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
+                        d3 ts; double offset;
+                        const int one = ck[j];
+                        mesh_closest_exact(a.sc.meshes[in.mesh], f.subdivision, si, di, &one, 1, &bt, &ts, &offset, &xc);
+                        if (bt.k < 0) continue;
+                        const double rf = dadd(bt.rf, offset);                    // SpatialSubdivision.cs:416
+                        // nearest over instances, ties to the lowest instance, then the lowest triangle index
+                        if (rf < eh.rf || (rf == eh.rf && (i < eh.inst || (i == eh.inst && bt.index < eh.index)))) {
+                            eh.hit = true; eh.inst = i; eh.k = bt.k; eh.index = bt.index; eh.rf_from_clip = bt.rf; eh.rf = rf;
+                            eh.clipped_start = ts; eh.dir = di;
+                        }
+                    }
+                    if (n_list > 1) xc.filter_unsure++;
+                }
+            }
+        }
+        // the rays the search could not bracket go to the fallback kernel, compacted
+        {
+            const uint32_t at = warp_append(&a.b.counts->n_fallback[a.fb_slot], undecided);
+            if (undecided) a.b.fallback[at] = r;
+        }
+        spawn_from_hit<SRC>(a, insts, active && !undecided, eh.hit, eh, sample, depth, &n_shaded, &n_shadow, &n_secondary, &n_hits);
+    }
+    const unsigned long long v[12] = {n_primary, n_shadow, n_secondary, xc.node_visits, xc.prim_tests, 0, n_hits, n_shaded, 0, xc.filter_unsure, 0, 0};
+    flush_counters(a.counters, v);
+}
+
+// The rays of the fallback list through the full reference-arithmetic search (closest_hit with the filter off:
+// exact BVH walk behind the full root-box clip), then the same continuation.
+template <int SRC>
+__global__ void __launch_bounds__(kWaveThreads) k_fallback(const __grid_constant__ WaveArgs a)
+{
+    const DevFrame& f = a.f;
+    const DevInstance* __restrict__ insts = a.insts;
+    int walk_stack[kStackEntries];
+    XCounters xc; xc.stack = walk_stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0;
+    xc.filter_unsure = 0; xc.filter_mismatch = 0;
+    unsigned int n_shadow = 0, n_secondary = 0, n_hits = 0, n_shaded = 0;
+    const uint32_t n = __ldg(&a.b.counts->n_fallback[a.fb_slot]);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t q = base + lane_id();
+        const bool active = q < n;
+        d3 s = mk(0, 0, 0), dir = mk(0, 0, 0); uint32_t sample = 0, depth = 0;
+        ExactHit eh; eh.hit = false; eh.inst = 0; eh.k = -1; eh.index = 0x7fffffff; eh.rf = kNoHit; eh.rf_from_clip = 0.0;
+        eh.clipped_start = s; eh.dir = dir;
+        if (active) {
+            const uint32_t r = a.b.fallback[q];
+            batch_ray<SRC>(a, insts, r, &s, &dir, &sample, &depth);
+            eh.dir = dir;
+            for (int i = 0; i < f.n_instances; i++) {
+                const DevInstance& in = insts[i];
+                const DevMesh& m = a.sc.meshes[in.mesh];
+                const d3 si = f.n_instances == 1 ? s : mk(in.start[0], in.start[1], in.start[2]);
+                const d3 di = f.n_instances == 1 ? dir : mul3x3(in.Minv, dir);
+                BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
+                d3 ts; double offset;
+                if (m.n_tris <= 0) continue;
+                mesh_closest_exact(m, f.subdivision, si, di, nullptr, 0, &bt, &ts, &offset, &xc);
+                if (bt.k < 0) continue;
+                const double rf = dadd(bt.rf, offset);
+                if (rf < eh.rf) {                                                 // strict: the lowest instance keeps a tie
+                    eh.hit = true; eh.inst = i; eh.k = bt.k; eh.index = bt.index; eh.rf_from_clip = bt.rf; eh.rf = rf;
+                    eh.clipped_start = ts; eh.dir = di;
+                }
+            }
+        }
+        spawn_from_hit<SRC>(a, insts, active, eh.hit, eh, sample, depth, &n_shaded, &n_shadow, &n_secondary, &n_hits);
+    }
+    const unsigned long long v[12] = {0, n_shadow, n_secondary, xc.node_visits, xc.prim_tests, 0, n_hits, n_shaded, 0, 0, 0, 0};
+    flush_counters(a.counters, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shadow: ShadowMethod.TraceRaysForSoftShadows (ShadowMethod.cs:144-180) over the compacted shading points
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWaveThreads) k_shadow(const __grid_constant__ WaveArgs a)
+{
+    const DevFrame& f = a.f;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_offsets = reinterpret_cast<double*>(smem_raw);
+    for (int i = threadIdx.x; i < 3 * f.shadow_samples; i += blockDim.x) s_offsets[i] = a.offsets[i];
+    __shared__ unsigned int s_bundle_score[2];
+    __shared__ uint32_t s_group;
+    if (threadIdx.x == 0) { s_bundle_score[0] = 0u; s_bundle_score[1] = 0u; }
+    __syncthreads();
+    const DevInstance* __restrict__ insts = a.insts;
+    int walk_stack[kStackEntries];
+    Counters c; c.node_visits = 0; c.prim_tests = 0; c.sphere_tests = 0; c.shaded = 0; c.filter_tests = 0; c.filter_unsure = 0;
+    c.filter_mismatch = 0; c.bundled = 0; c.bundle_skip = 0; c.stack = walk_stack;
+    const uint32_t n_items = __ldg(&a.b.counts->n_shadow);
+    const int n = f.shadow_samples;
+    // a warp takes 32 consecutive shading points (neighbouring pixels: their rays towards sample i of the light run
+    // side by side) and walks the n samples with them; warps fetch their groups from a queue
+    for (;;) {
+        uint32_t group = 0;
+        if (lane_id() == 0) group = atomicAdd(&a.b.counts->shadow_head, 1u);
+        group = __shfl_sync(0xffffffffu, group, 0);
+        if ((unsigned long long)group * 32ull >= n_items) break;
+        const uint32_t q = group * 32u + lane_id();
+        const bool active = q < n_items;
+        d3 end = mk(0, 0, 0); uint32_t slot = 0, inst = 0;
+        if (active) {
+            const ShadowItem* it = a.b.shadow + q;
+            const double2 v0 = ldg2(it, 0);
+            const double v1 = __ldg(reinterpret_cast<const double*>(it) + 2);
+            const uint2 si = __ldg(reinterpret_cast<const uint2*>(it) + 3);
+            end = mk(v0.x, v0.y, v1); slot = si.x; inst = si.y;
+        }
+        const DevInstance& in = insts[inst];
+        const DevMesh& m = a.sc.meshes[in.mesh];
+        int escaped = 0;
+        bool all_clear = false;
+        if (active && f.point_lighting && f.bundle_budget > 0) {
+            // (the block keeps the score of the cone walks: shade_and_shadow in sr_render.cu)
+            const unsigned int ok = s_bundle_score[0], bad = s_bundle_score[1];
+            c.bundle_skip++;
+            if (bad < 64u || ok * 32u >= bad || (c.bundle_skip & 255) == 0) {
+                const d3 light = mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]);
+                all_clear = bundle_clear(m, end, light, f.light_radius, f.bundle_budget, &c);
+                if (all_clear) c.bundled += (unsigned int)n;
+                atomicAdd(&s_bundle_score[all_clear ? 0 : 1], 1u);
+            }
+        }
+        if (all_clear) escaped = n;
+        const bool walk_rays = active && !all_clear;
+        for (int i = 0; i < n; i++) {
+            bool unsure = false;
+            ShadowFallback fb;
+            if (walk_rays) {
+                d3 start, dir;
+                shadow_ray(f, in, s_offsets, end, i, &start, &dir);
+                const d3 anchor = f.point_lighting ? end : vadd(start, dir);   // the ray's far end
+                FRay r;
+                int list[kMaxCand] = {-1, -1, -1, -1}; int n_list = 0;
+                int res = fray_setup(m, f.subdivision, anchor, dir, &r);
+                if (res == 1) res = walk_filter_any(m.nodes, m.filt, m.n_tris, r, m.scale, list, &n_list, &c);
+                if (res == 2) {
+                    // the reference arithmetic looks at the triangles the filter could not decide (all of them when
+                    // they are too many to list): shadow_fallback
+                    c.filter_unsure++;
+                    unsure = true;
+                    fb.item = q; fb.sample = (uint32_t)i;
+                    const bool listed = n_list >= 1 && n_list <= kMaxCand;
+                    fb.list[0] = listed ? list[0] : -2; fb.list[1] = listed && n_list > 1 ? list[1] : -1;
+                    fb.list[2] = listed && n_list > 2 ? list[2] : -1; fb.list[3] = listed && n_list > 3 ? list[3] : -1;
+                } else if (res == 0) {
+                    escaped++;
+                }
+            }
+            if (__any_sync(0xffffffffu, unsure)) {
+                const uint32_t at = warp_append(&a.b.counts->n_shadow_fallback, unsure);
+                if (unsure) {
+                    if (at < a.cap_shadow_fallback) a.b.shadow_fallback[at] = fb;
+                    else {
+                        // the list is full (it holds one entry per sample of the chunk): answer this ray here
+                        d3 start, dir;
+                        shadow_ray(f, in, s_offsets, end, i, &start, &dir);
+                        int list[kMaxCand]; int n_list = 0;
+                        for (int j = 0; j < kMaxCand; j++) if (fb.list[j] >= 0) list[n_list++] = fb.list[j];
+                        XCounters xc; xc.stack = walk_stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0;
+                        xc.filter_unsure = 0; xc.filter_mismatch = 0;
+                        if (!occluded_mesh(m, f.subdivision, start, dir, n_list ? list : nullptr, n_list, &xc)) escaped++;
+                        c.node_visits += xc.node_visits; c.prim_tests += xc.prim_tests;
+                    }
+                }
+            }
+        }
+        if (active) a.b.slot_escaped[slot] = (uint32_t)escaped;
+    }
+    const unsigned long long v[12] = {0, 0, 0, c.node_visits, c.prim_tests, 0, 0, 0, c.filter_tests, c.filter_unsure, 0, c.bundled};
+    flush_counters(a.counters, v);
+}
+
+__global__ void __launch_bounds__(kWaveThreads) k_shadow_fallback(const __grid_constant__ WaveArgs a)
+{
+    const DevFrame& f = a.f;
+    const DevInstance* __restrict__ insts = a.insts;
+    int walk_stack[kStackEntries];
+    XCounters xc; xc.stack = walk_stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0;
+    xc.filter_unsure = 0; xc.filter_mismatch = 0;
+    const uint32_t n = min(__ldg(&a.b.counts->n_shadow_fallback), a.cap_shadow_fallback);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const ShadowFallback fb = a.b.shadow_fallback[q];
+        const ShadowItem it = a.b.shadow[fb.item];
+        const DevInstance& in = insts[it.inst];
+        const DevMesh& m = a.sc.meshes[in.mesh];
+        d3 start, dir;
+        shadow_ray(f, in, a.offsets, mk(it.end[0], it.end[1], it.end[2]), (int)fb.sample, &start, &dir);
+        int list[kMaxCand]; int n_list = 0;
+        for (int j = 0; j < kMaxCand; j++) if (fb.list[j] >= 0) list[n_list++] = fb.list[j];
+        const bool occ = occluded_mesh(m, f.subdivision, start, dir, n_list ? list : nullptr, n_list, &xc);
+        if (!occ) atomicAdd(&a.b.slot_escaped[it.slot], 1u);
+    }
+    const unsigned long long v[12] = {0, 0, 0, xc.node_visits, xc.prim_tests, 0, 0, 0, 0, 0, 0, 0};
+    flush_counters(a.counters, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// compose: shadow byte, mirror blend chain, sub-pixel sums, Surface.DrawPixel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWaveThreads) k_compose(const __grid_constant__ WaveArgs a, uint32_t* __restrict__ pixels,
+                                                         int32_t* __restrict__ hit_ids)
+{
+    const DevFrame& f = a.f;
+    const int n = f.sub_pixel_res, nn = n * n;
+    const uint32_t S = a.n_samples;
+    const uint32_t n_px = a.n_tiles * 32u;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_px) return;
+    const int t = (int)(p >> 5), px = (int)(p & 31u);
+    const int tile = a.tile0 + t;
+    const int ty = tile / f.tiles_x, tx = tile - ty * f.tiles_x;
+    const int band_j = ty / f.tiles_per_band;
+    const int row0 = f.start_row + (f.band_index + band_j * f.band_count) * f.band_height;
+    const int band_r = (ty - band_j * f.tiles_per_band) * 4 + (px >> 3);
+    const int col = tx * 8 + (px & 7), row = row0 + band_r;
+    if (col >= f.width || band_r >= f.band_height || row > f.end_row) return;
+    int sum_r = 0, sum_g = 0, sum_b = 0, id = -1;
+    for (int si = 0; si < nn; si++) {
+        const uint32_t s = (uint32_t)t * 32u * (uint32_t)nn + (uint32_t)(px * nn + si);
+        const uint32_t st = a.b.sample_state[s];
+        const int n_hits = (int)(st & 7u);
+        uint32_t acc = f.background;
+        if (n_hits > 0) {
+            uint32_t local[5];
+            for (int k = 0; k < n_hits; k++) {
+                uint32_t color = a.b.slot_color[(uint32_t)k * S + s];
+                if (f.shadows) {
+                    const uint32_t escaped = a.b.slot_escaped[(uint32_t)k * S + s];
+                    const double frac = ddiv((double)escaped, (double)f.shadow_samples);   // ShadowMethod.cs:178
+                    color = modulate(color, to_byte(dmul(frac, 255.0)));
+                }
+                local[k] = color;
+            }
+            acc = (st & 8u) ? mirror_blend(local[n_hits - 1], f.background) : local[n_hits - 1];
+            for (int k = n_hits - 2; k >= 0; k--) acc = mirror_blend(local[k], acc);
+            if (si == nn - 1) id = a.b.sample_id[s];
+        }
+        sum_r += (int)((acc >> 16) & 0xff); sum_g += (int)((acc >> 8) & 0xff); sum_b += (int)(acc & 0xff);
+    }
+    sum_r /= nn; sum_g /= nn; sum_b /= nn;                                       // Renderer.cs:1820-1822
+    const size_t idx = (size_t)row * (size_t)f.width + (size_t)col;
+    pixels[idx] = 0xff000000u | ((uint32_t)(sum_r & 0xff) << 16) | ((uint32_t)(sum_g & 0xff) << 8) | (uint32_t)(sum_b & 0xff);
+    if (hit_ids) hit_ids[idx] = id;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side: buffers and the launch sequence of one frame
+// ---------------------------------------------------------------------------------------------
+size_t wave_buffer_bytes(uint32_t cap_samples, int max_depth_slots, WaveLayout* lay)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+    const size_t S = cap_samples;
+    lay->counts = take(sizeof(WaveCounts));
+    lay->cand = take(S * sizeof(int4));
+    lay->meta = take(S * sizeof(uint32_t));
+    lay->slot_color = take(S * (size_t)max_depth_slots * sizeof(uint32_t));
+    lay->slot_escaped = take(S * (size_t)max_depth_slots * sizeof(uint32_t));
+    lay->sample_state = take(S);
+    lay->sample_id = take(S * sizeof(int32_t));
+    lay->ref0 = take(S * sizeof(RefRay));
+    lay->ref1 = take(S * sizeof(RefRay));
+    lay->shadow = take(S * (size_t)max_depth_slots * sizeof(ShadowItem));
+    lay->fallback = take(S * sizeof(uint32_t));
+    lay->shadow_fallback = take(S * sizeof(ShadowFallback));      // (capacity checked by the host against the count: see wave_render)
+    return off;
+}
+
+void wave_bind(void* base, const WaveLayout& lay, WaveBufs* b)
+{
+    unsigned char* p = static_cast<unsigned char*>(base);
+    b->counts = reinterpret_cast<WaveCounts*>(p + lay.counts);
+    b->cand = reinterpret_cast<int4*>(p + lay.cand);
+    b->meta = reinterpret_cast<uint32_t*>(p + lay.meta);
+    b->slot_color = reinterpret_cast<uint32_t*>(p + lay.slot_color);
+    b->slot_escaped = reinterpret_cast<uint32_t*>(p + lay.slot_escaped);
+    b->sample_state = reinterpret_cast<uint8_t*>(p + lay.sample_state);
+    b->sample_id = reinterpret_cast<int32_t*>(p + lay.sample_id);
+    b->ref[0] = reinterpret_cast<RefRay*>(p + lay.ref0);
+    b->ref[1] = reinterpret_cast<RefRay*>(p + lay.ref1);
+    b->shadow = reinterpret_cast<ShadowItem*>(p + lay.shadow);
+    b->fallback = reinterpret_cast<uint32_t*>(p + lay.fallback);
+    b->shadow_fallback = reinterpret_cast<ShadowFallback*>(p + lay.shadow_fallback);
+}
+
+int wave_max_depth_slots() { return 5; }
+
+// One frame: every chunk of tiles through the stage kernels.  Everything is stream-ordered; nothing synchronises.
+cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets, const WaveBufs& bufs,
+                        uint32_t cap_samples, uint32_t* d_pixels, int32_t* d_ids, DevCounters* d_counters, int sm_count,
+                        cudaStream_t stream, int* launches)
+{
+    const int nn = f.sub_pixel_res * f.sub_pixel_res;
+    const uint32_t per_tile = 32u * (uint32_t)nn;
+    const long long n_tiles = (long long)f.tiles_x * f.tiles_y;
+    const uint32_t tiles_per_chunk = cap_samples / per_tile;
+    if (tiles_per_chunk == 0) return cudaErrorInvalidValue;
+    const int bounces = (f.reflection_depth > 0 && f.n_instances == 1) ? f.reflection_depth : 0;
+    const size_t smem_shadow = sizeof(double) * 3 * (size_t)(f.shadows ? f.shadow_samples : 0);
+    if (smem_shadow > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shadow);
+        if (e != cudaSuccess) return e;
+    }
+    const int persistent = sm_count * 8;          // grid of the list kernels (grid-stride over a device-side count)
+    int n_launch = 0;
+    for (long long tile0 = 0; tile0 < n_tiles; tile0 += tiles_per_chunk) {
+        WaveArgs a;
+        a.f = f; a.sc = sc; a.insts = d_insts; a.offsets = d_offsets; a.b = bufs; a.counters = d_counters;
+        a.tile0 = (int)tile0;
+        a.n_tiles = (uint32_t)((n_tiles - tile0) < (long long)tiles_per_chunk ? (n_tiles - tile0) : (long long)tiles_per_chunk);
+        a.n_samples = a.n_tiles * per_tile;
+        a.n_rays = a.n_samples;
+        a.ref_in = 0; a.ref_out = 0; a.fb_slot = 0;
+        a.cap_shadow_fallback = cap_samples;
+        cudaError_t e = cudaMemsetAsync(bufs.counts, 0, sizeof(WaveCounts), stream);
+        if (e != cudaSuccess) return e;
+        const int grid_cam = (int)((a.n_rays + kWaveThreads - 1) / kWaveThreads);
+        k_search<0><<<grid_cam, kWaveThreads, 0, stream>>>(a);
+        k_hit<0><<<grid_cam, kWaveThreads, 0, stream>>>(a);
+        k_fallback<0><<<sm_count, kWaveThreads, 0, stream>>>(a);
+        n_launch += 3;
+        for (int depth = 1; depth <= bounces; depth++) {
+            a.ref_in = (depth - 1) & 1; a.ref_out = depth & 1; a.fb_slot = depth;
+            // (the list written two bounces ago is consumed: its counter restarts)
+            e = cudaMemsetAsync(&bufs.counts->n_ref[a.ref_out], 0, sizeof(uint32_t), stream);
+            if (e != cudaSuccess) return e;
+            k_search<1><<<persistent, kWaveThreads, 0, stream>>>(a);
+            k_hit<1><<<persistent, kWaveThreads, 0, stream>>>(a);
+            k_fallback<1><<<sm_count, kWaveThreads, 0, stream>>>(a);
+            n_launch += 3;
+        }
+        if (f.shadows) {
+            k_shadow<<<persistent, kWaveThreads, smem_shadow, stream>>>(a);
+            k_shadow_fallback<<<sm_count, kWaveThreads, 0, stream>>>(a);
+            n_launch += 2;
+        }
+        k_compose<<<(int)((a.n_tiles * 32u + kWaveThreads - 1) / kWaveThreads), kWaveThreads, 0, stream>>>(a, d_pixels, d_ids);
+        n_launch += 1;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (launches) *launches = n_launch;
+    return cudaSuccess;
+}
+
+}  // namespace sr

@@ -16,8 +16,8 @@ from .scene import FrameParams, MeshData, SceneDescHolder, SphereData
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libsoftray_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["sr_api.cu", "sr_render.cu", "sr_diag.cu", "sr_bvh.cpp", "sr_model3ds.cpp", "sr_resolve.cu", "sr_lbvh.cu"]
-HEADERS = ["sr_types.h", "sr_bvh.h", os.path.join("..", "..", "include", "softray_cuda.h")]
+SOURCES = ["sr_api.cu", "sr_render.cu", "sr_diag.cu", "sr_bvh.cpp", "sr_model3ds.cpp", "sr_resolve.cu", "sr_lbvh.cu", "sr_wave.cu"]
+HEADERS = ["sr_types.h", "sr_bvh.h", "sr_device.cuh", "sr_wave.h", os.path.join("..", "..", "include", "softray_cuda.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
     "-Xcompiler", "-fPIC,-ffp-contract=off",

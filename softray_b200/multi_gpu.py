@@ -94,6 +94,7 @@ class PeerFramebuffer:
         import torch.distributed as dist
 
         self.ctx = ctx
+        self.group = group
         self.nbytes = int(width) * int(height) * 4
         self.rank = dist.get_rank(group)
         self.owner = self.rank == 0
@@ -107,11 +108,16 @@ class PeerFramebuffer:
         dist.barrier(group)
 
     def close(self):
+        """Collective: the importers unmap first (cudaIpcCloseMemHandle), every rank meets, only then does the
+        owner free -- freeing an exported allocation that a peer still has mapped is undefined behaviour."""
+        import torch.distributed as dist
+
         if getattr(self, "ptr", None):
+            if not self.owner:
+                self.ctx.ipc_close(self.ptr)
+            dist.barrier(self.group)
             if self.owner:
                 self.ctx.device_free(self.ptr)
-            else:
-                self.ctx.ipc_close(self.ptr)
             self.ptr = None
 
 
