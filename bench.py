@@ -277,7 +277,7 @@ def main():
     st = scene.render_device(frame, target_ptr, stream=stream.cuda_stream, want_stats=True, c_frame=c_frame)
     counters = {k: getattr(st, k) for k in ("rays_primary", "rays_shadow", "rays_secondary", "node_visits", "prim_tests",
                                             "sphere_tests", "hits_primary", "shaded_hits", "filter_tests", "filter_unsure",
-                                            "rays_bundled")}
+                                            "rays_bundled", "rays_fallback")}
     if dist is not None:
         t = torch.tensor([counters[k] for k in sorted(counters)], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)

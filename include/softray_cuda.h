@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SOFTRAY_ABI_VERSION 3
+#define SOFTRAY_ABI_VERSION 4
 #define SOFTRAY_MAX_INSTANCES 128   /* instances per frame (composite extension) */
 #define SOFTRAY_MAX_SHADOW_SAMPLES 1024
 
@@ -197,6 +197,9 @@ typedef struct softray_stats {
     uint64_t filter_mismatch;  /* SOFTRAY_FILTER_VERIFY: sure filter answers the FP64 path contradicts */
     uint64_t rays_bundled;     /* of rays_shadow: answered together, one conservative cone test per
                                   shading point proving that no triangle can occlude any of its rays */
+    uint64_t rays_fallback;    /* camera / reflection rays whose candidate search could not bracket the hit (more
+                                  than 4 candidate triangles, an axis-parallel direction ...): answered by the
+                                  full reference-arithmetic walk (stage-kernel pipeline only)               */
     double   ms_kernel;        /* CUDA-event time of the render kernel(s)                          */
     double   ms_h2d;           /* frame constants upload                                           */
     double   ms_d2h;           /* framebuffer (+hit ids) readback                                  */

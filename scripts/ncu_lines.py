@@ -61,7 +61,8 @@ ia, ii, isamp, ithr = hdr.index("Address"), hdr.index("Instructions Executed"), 
 stall_cols = [(k, h) for k, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 body = rows[1:]
 base = int(body[0][ia], 16)
-sec = next((v for k, v in sections.items() if "render_kernel" in k and kname.split("::")[-1] in k), None) or max(sections.values(), key=len)
+want = os.environ.get("NCU_SECTION")
+sec = (next((v for k, v in sections.items() if want in k), None) if want else None) or next((v for k, v in sections.items() if "render_kernel" in k and kname.split("::")[-1] in k), None) or max(sections.values(), key=len)
 
 by_line = defaultdict(lambda: [0, 0, 0])
 by_func = defaultdict(lambda: [0, 0, 0, defaultdict(int)])

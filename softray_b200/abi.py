@@ -5,7 +5,7 @@ against the values the C side reports through softray_abi_sizeof().
 """
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK = 0
 E_INVALID_ARG = -1
@@ -136,6 +136,7 @@ class Stats(C.Structure):
         ("filter_unsure", C.c_uint64),
         ("filter_mismatch", C.c_uint64),
         ("rays_bundled", C.c_uint64),
+        ("rays_fallback", C.c_uint64),
         ("ms_kernel", C.c_double),
         ("ms_h2d", C.c_double),
         ("ms_d2h", C.c_double),
@@ -150,7 +151,7 @@ class Stats(C.Structure):
         return self.rays_primary + self.rays_shadow + self.rays_secondary
 
 
-EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 192, "stats": 136}
+EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 192, "stats": 144}
 
 assert C.sizeof(Mesh) == EXPECTED_SIZES["mesh"]
 assert C.sizeof(Sphere) == EXPECTED_SIZES["sphere"]

@@ -84,7 +84,9 @@ struct softray_ctx {
     uint32_t wave_cap = 0;                      // samples per chunk the arena is laid out for
     int wave_slots = 0;                         // shading points per sample (1 + bounces)
     int last_launches = 1;                      // kernels the last frame launched (softray_stats.launches)
-    WaveBufs wave;
+    WaveBufs wave[2];                           // two chunks in flight (wave_render)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
 };
 
@@ -445,6 +447,9 @@ extern "C" void softray_destroy(softray_ctx* ctx)
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
     if (ctx->ev_frame) cudaEventDestroy(ctx->ev_frame);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -471,6 +476,9 @@ extern "C" int softray_create(int32_t device_ordinal, softray_ctx** out)
         for (auto& ev : ctx->ev) SR_CUDA(ctx, cudaEventCreate(&ev));
         SR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming));
         SR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_frame, cudaEventDisableTiming));
+        SR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        SR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        SR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_insts, sizeof(DevInstance) * SOFTRAY_MAX_INSTANCES));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_offsets, sizeof(double) * 3 * SOFTRAY_MAX_SHADOW_SAMPLES));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_tile_counter, sizeof(unsigned int)));
@@ -1007,27 +1015,29 @@ int enqueue_frame(softray_ctx* ctx, const softray_scene* scene, const Prepared& 
     if (p.wave) {
         const int nn = f.sub_pixel_res * f.sub_pixel_res;
         const int slots = 1 + ((f.reflection_depth > 0 && f.n_instances == 1) ? f.reflection_depth : 0);
-        const long long frame_samples = (long long)f.tiles_x * f.tiles_y * 32 * nn;
-        long long cap = env_int("SOFTRAY_WAVE_CHUNK", 1 << 23);
-        if (cap > frame_samples) cap = frame_samples;
-        if (cap < 32LL * nn) cap = 32LL * nn;
-        cap = cap / (32LL * nn) * (32LL * nn);
+        // samples per chunk: SOFTRAY_WAVE_CHUNK (default 8 M), at most half the frame (two chunks in flight), whole tiles
+        const long long per_tile = 32LL * nn, frame_tiles = (long long)f.tiles_x * f.tiles_y;
+        long long cap_tiles = env_int("SOFTRAY_WAVE_CHUNK", 1 << 23) / per_tile;
+        if (cap_tiles > (frame_tiles + 1) / 2) cap_tiles = (frame_tiles + 1) / 2;
+        if (cap_tiles < 1) cap_tiles = 1;
+        const long long cap = cap_tiles * per_tile;
         if (ctx->wave_cap < (uint32_t)cap || ctx->wave_slots < slots) {
             // (grow only: frames of one host keep their size; a bigger frame reallocates once)
             SR_CUDA(ctx, cudaStreamSynchronize(stream));
             if (ctx->stream != stream) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->wave_base); ctx->wave_base = nullptr; ctx->wave_cap = 0; ctx->wave_bytes = 0;
             const uint32_t new_cap = (uint32_t)std::max<long long>(cap, ctx->wave_cap);
             const int new_slots = std::max(slots, ctx->wave_slots);
+            cudaFree(ctx->wave_base); ctx->wave_base = nullptr; ctx->wave_cap = 0; ctx->wave_bytes = 0;
             WaveLayout lay;
             const size_t bytes = wave_buffer_bytes(new_cap, new_slots, &lay);
-            SR_CUDA(ctx, cudaMalloc(&ctx->wave_base, bytes));
-            wave_bind(ctx->wave_base, lay, &ctx->wave);
-            ctx->wave_bytes = bytes; ctx->wave_cap = new_cap; ctx->wave_slots = new_slots;
+            SR_CUDA(ctx, cudaMalloc(&ctx->wave_base, 2 * bytes));
+            wave_bind(ctx->wave_base, lay, &ctx->wave[0]);
+            wave_bind(static_cast<unsigned char*>(ctx->wave_base) + bytes, lay, &ctx->wave[1]);
+            ctx->wave_bytes = 2 * bytes; ctx->wave_cap = new_cap; ctx->wave_slots = new_slots;
         }
         int launches = 0;
         SR_CUDA(ctx, wave_render(f, scene->dev, ctx->d_insts, ctx->d_offsets, ctx->wave, (uint32_t)cap, d_pixels, d_ids, ctx->d_counters,
-                                 ctx->sm_count, stream, &launches));
+                                 ctx->sm_count, stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join, &launches));
         ctx->last_launches = launches;
     } else
     SR_CUDA(ctx, launch_render(f, scene->dev, ctx->d_insts, ctx->d_offsets, d_pixels, d_ids, ctx->d_tile_counter,
@@ -1048,7 +1058,7 @@ int collect_stats(softray_ctx* ctx, cudaStream_t stream, softray_stats* st, bool
     st->node_visits = c.node_visits; st->prim_tests = c.prim_tests; st->sphere_tests = c.sphere_tests;
     st->hits_primary = c.hits_primary; st->shaded_hits = c.shaded_hits;
     st->filter_tests = c.filter_tests; st->filter_unsure = c.filter_unsure; st->filter_mismatch = c.filter_mismatch;
-    st->rays_bundled = c.rays_bundled;
+    st->rays_bundled = c.rays_bundled; st->rays_fallback = c.rays_fallback;
     st->launches = (uint64_t)ctx->last_launches;
     float ms = 0.f;
     SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); st->ms_h2d = ms;

@@ -353,6 +353,9 @@ __device__ __forceinline__ float cull_from(double limit, double t_off)
 // triangles, so waiting for every lane to reach a leaf costs more than it saves.
 // The thread's single stack is passed in (Counters::stack); returns the number of nodes visited.
 // ---------------------------------------------------------------------------------------------
+#ifndef SR_WALK_MODE
+#define SR_WALK_MODE 0     // 0: one node or one leaf per iteration ("if-if"); 1: "while-while" (the stage kernels)
+#endif
 template <class BOX, class LEAF>
 __device__ __forceinline__ unsigned int walk_bvh(const BvhNode* __restrict__ nodes, int n_prims, int* __restrict__ stack, BOX box,
                                                  LEAF leaf)
@@ -363,6 +366,43 @@ __device__ __forceinline__ unsigned int walk_bvh(const BvhNode* __restrict__ nod
     int sp = 0;
     int cur = 0;
     unsigned int nv = 0;
+#if SR_WALK_MODE == 1
+    // "while-while": every lane descends until it holds a leaf (or has nothing left), then the lanes of the warp
+    // test their leaves TOGETHER.  In the if-if form the leaf code runs whenever some lane happens to reach a leaf:
+    // with 4 of 32 lanes on average (profiles/r02a_*), a quarter of all issue slots at 12 % lane utilisation.
+    constexpr int kDone = (int)0x80000000;
+    for (;;) {
+        while (cur >= 0) {
+            const float4* p = reinterpret_cast<const float4*>(nodes + cur);
+            const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
+            const int2 d = __ldg(reinterpret_cast<const int2*>(p + 3));
+            nv++;
+            float t0, t1;
+            const bool h0 = box(a.x, a.y, a.z, a.w, b.x, b.y, &t0);
+            const bool h1 = box(b.z, b.w, cc.x, cc.y, cc.z, cc.w, &t1);
+            if (h0 && h1) {
+                const bool first0 = t0 <= t1;
+                const int far = first0 ? d.y : d.x;
+                stack[sp++] = far;
+#if SR_PREFETCH >= 1
+                if (far >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + far));
+#endif
+                cur = first0 ? d.x : d.y;
+            } else if (h0) {
+                cur = d.x;
+            } else if (h1) {
+                cur = d.y;
+            } else {
+                cur = sp > 0 ? stack[--sp] : kDone;
+            }
+        }
+        if (cur == kDone) break;
+        const int code = -1 - cur;
+        if (leaf(code >> 4, code & 15)) break;
+        cur = sp > 0 ? stack[--sp] : kDone;
+        if (cur == kDone) break;
+    }
+#else
     for (;;) {
         if (cur >= 0) {
             const float4* p = reinterpret_cast<const float4*>(nodes + cur);
@@ -392,6 +432,7 @@ __device__ __forceinline__ unsigned int walk_bvh(const BvhNode* __restrict__ nod
         if (sp == 0) break;
         cur = stack[--sp];
     }
+#endif
     return nv;
 }
 

@@ -19,8 +19,16 @@
 // Every stage keeps the fused kernel's arithmetic, so frames are identical bit for bit (tests/test_cuda_wave.py
 // requires wave == fused == oracle).  Replaces RaytraceBlock -> TraceRayComplex -> IRayIntersectable.IntersectRay ->
 // Surface.DrawPixel (Engine3D/Renderer.cs:1690-1925 and the Raytrace/*Method.cs decorators), like sr_render.cu.
+#ifndef SR_WAVE_WALK_MODE
+#define SR_WAVE_WALK_MODE 0      // traversal loop of the stage kernels: 0 if-if, 1 while-while (measured: config3 41.2 -> 48.4 ms, config5 14.5 -> 15.0)
+#endif
+#define SR_WALK_MODE SR_WAVE_WALK_MODE
 #include "sr_device.cuh"
 #include "sr_wave.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 namespace sr {
 
@@ -42,10 +50,10 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool want)
     return base + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u));
 }
 
-__device__ __forceinline__ void flush_counters(DevCounters* counters, const unsigned long long (&v)[12])
+__device__ __forceinline__ void flush_counters(DevCounters* counters, const unsigned long long (&v)[13])
 {
 #pragma unroll
-    for (int k = 0; k < 12; k++) {
+    for (int k = 0; k < 13; k++) {
         unsigned long long x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane_id() == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + k, x);
@@ -179,8 +187,8 @@ __device__ __forceinline__ void search_mesh(const DevMesh& m, int subdivision, d
     }
 }
 
-template <int SRC>
-__global__ void __launch_bounds__(kWaveThreads) k_search(const __grid_constant__ WaveArgs a)
+template <int SRC, int MINB>
+__global__ void __launch_bounds__(kWaveThreads, MINB) k_search(const __grid_constant__ WaveArgs a)
 {
     const DevFrame& f = a.f;
     const DevInstance* __restrict__ insts = a.insts;
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_search(const __grid_constant__
         a.b.cand[r] = cand;
         a.b.meta[r] = state | insts_of;
     }
-    const unsigned long long v[12] = {0, 0, 0, xc.node_visits, 0, 0, 0, 0, xc.filter_tests, 0, 0, 0};
+    const unsigned long long v[13] = {0, 0, 0, xc.node_visits, 0, 0, 0, 0, xc.filter_tests, 0, 0, 0, 0};
     flush_counters(a.counters, v);
 }
 
@@ -330,15 +338,15 @@ __device__ __forceinline__ void spawn_from_hit(const WaveArgs& a, const DevInsta
     }
 }
 
-template <int SRC>
-__global__ void __launch_bounds__(kWaveThreads) k_hit(const __grid_constant__ WaveArgs a)
+template <int SRC, int MINB>
+__global__ void __launch_bounds__(kWaveThreads, MINB) k_hit(const __grid_constant__ WaveArgs a)
 {
     const DevFrame& f = a.f;
     const DevInstance* __restrict__ insts = a.insts;
     int walk_stack[4];                  // (the listed-candidate evaluators never walk)
     XCounters xc; xc.stack = walk_stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0;
     xc.filter_unsure = 0; xc.filter_mismatch = 0;
-    unsigned int n_primary = 0, n_shadow = 0, n_secondary = 0, n_hits = 0, n_shaded = 0;
+    unsigned int n_primary = 0, n_shadow = 0, n_secondary = 0, n_hits = 0, n_shaded = 0, n_undecided = 0;
     const uint32_t n_rays = SRC == 0 ? a.n_rays : __ldg(&a.b.counts->n_ref[a.ref_in]);
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_rays; base += stride) {
@@ -357,7 +365,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_hit(const __grid_constant__ Wa
         bool undecided = false;
         if (active) {
             if (SRC == 0) n_primary++;
-            if (state == kStateUndecided) { undecided = true; xc.filter_unsure++; }
+            if (state == kStateUndecided) { undecided = true; xc.filter_unsure++; n_undecided++; }
             else if (state == kStateListed) {
                 const int4 cv = a.b.cand[r];
                 const int ck[kMaxCand] = {cv.x, cv.y, cv.z, cv.w};
@@ -407,7 +415,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_hit(const __grid_constant__ Wa
         }
         spawn_from_hit<SRC>(a, insts, active && !undecided, eh.hit, eh, sample, depth, &n_shaded, &n_shadow, &n_secondary, &n_hits);
     }
-    const unsigned long long v[12] = {n_primary, n_shadow, n_secondary, xc.node_visits, xc.prim_tests, 0, n_hits, n_shaded, 0, xc.filter_unsure, 0, 0};
+    const unsigned long long v[13] = {n_primary, n_shadow, n_secondary, xc.node_visits, xc.prim_tests, 0, n_hits, n_shaded, 0, xc.filter_unsure, 0, 0, n_undecided};
     flush_counters(a.counters, v);
 }
 
@@ -453,14 +461,15 @@ __global__ void __launch_bounds__(kWaveThreads) k_fallback(const __grid_constant
         }
         spawn_from_hit<SRC>(a, insts, active, eh.hit, eh, sample, depth, &n_shaded, &n_shadow, &n_secondary, &n_hits);
     }
-    const unsigned long long v[12] = {0, n_shadow, n_secondary, xc.node_visits, xc.prim_tests, 0, n_hits, n_shaded, 0, 0, 0, 0};
+    const unsigned long long v[13] = {0, n_shadow, n_secondary, xc.node_visits, xc.prim_tests, 0, n_hits, n_shaded, 0, 0, 0, 0, 0};
     flush_counters(a.counters, v);
 }
 
 // ---------------------------------------------------------------------------------------------
 // shadow: ShadowMethod.TraceRaysForSoftShadows (ShadowMethod.cs:144-180) over the compacted shading points
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWaveThreads) k_shadow(const __grid_constant__ WaveArgs a)
+template <int MINB>
+__global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_constant__ WaveArgs a)
 {
     const DevFrame& f = a.f;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -554,7 +563,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_shadow(const __grid_constant__
         }
         if (active) a.b.slot_escaped[slot] = (uint32_t)escaped;
     }
-    const unsigned long long v[12] = {0, 0, 0, c.node_visits, c.prim_tests, 0, 0, 0, c.filter_tests, c.filter_unsure, 0, c.bundled};
+    const unsigned long long v[13] = {0, 0, 0, c.node_visits, c.prim_tests, 0, 0, 0, c.filter_tests, c.filter_unsure, 0, c.bundled, 0};
     flush_counters(a.counters, v);
 }
 
@@ -578,7 +587,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_shadow_fallback(const __grid_c
         const bool occ = occluded_mesh(m, f.subdivision, start, dir, n_list ? list : nullptr, n_list, &xc);
         if (!occ) atomicAdd(&a.b.slot_escaped[it.slot], 1u);
     }
-    const unsigned long long v[12] = {0, 0, 0, xc.node_visits, xc.prim_tests, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned long long v[13] = {0, 0, 0, xc.node_visits, xc.prim_tests, 0, 0, 0, 0, 0, 0, 0, 0};
     flush_counters(a.counters, v);
 }
 
@@ -675,60 +684,156 @@ void wave_bind(void* base, const WaveLayout& lay, WaveBufs* b)
 
 int wave_max_depth_slots() { return 5; }
 
-// One frame: every chunk of tiles through the stage kernels.  Everything is stream-ordered; nothing synchronises.
-cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets, const WaveBufs& bufs,
+namespace {
+int env_occ(const char* name, int dflt)
+{
+    const char* e = std::getenv(name);
+    const int v = (e && *e) ? std::atoi(e) : dflt;
+    return v < 1 ? 1 : (v > 6 ? 6 : v);
+}
+template <int SRC>
+void launch_search(int occ, int grid, cudaStream_t st, const WaveArgs& a)
+{
+    switch (occ) {
+    case 2: k_search<SRC, 2><<<grid, kWaveThreads, 0, st>>>(a); break;
+    case 3: k_search<SRC, 3><<<grid, kWaveThreads, 0, st>>>(a); break;
+    case 4: k_search<SRC, 4><<<grid, kWaveThreads, 0, st>>>(a); break;
+    case 5: k_search<SRC, 5><<<grid, kWaveThreads, 0, st>>>(a); break;
+    default: k_search<SRC, 6><<<grid, kWaveThreads, 0, st>>>(a); break;
+    }
+}
+template <int SRC>
+void launch_hit(int occ, int grid, cudaStream_t st, const WaveArgs& a)
+{
+    switch (occ) {
+    case 2: k_hit<SRC, 2><<<grid, kWaveThreads, 0, st>>>(a); break;
+    case 3: k_hit<SRC, 3><<<grid, kWaveThreads, 0, st>>>(a); break;
+    default: k_hit<SRC, 4><<<grid, kWaveThreads, 0, st>>>(a); break;
+    }
+}
+cudaError_t launch_shadow(int occ, int grid, size_t smem, cudaStream_t st, const WaveArgs& a)
+{
+#define SR_SHADOW_CASE(N)                                                                                                   \
+    case N:                                                                                                                 \
+        if (smem > 48 * 1024) {                                                                                             \
+            cudaError_t e = cudaFuncSetAttribute(k_shadow<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+            if (e != cudaSuccess) return e;                                                                                 \
+        }                                                                                                                   \
+        k_shadow<N><<<grid, kWaveThreads, smem, st>>>(a);                                                                   \
+        break;
+    switch (occ) {
+        SR_SHADOW_CASE(2) SR_SHADOW_CASE(3) SR_SHADOW_CASE(4) SR_SHADOW_CASE(5)
+    default:
+        SR_SHADOW_CASE(6)
+    }
+#undef SR_SHADOW_CASE
+    return cudaSuccess;
+}
+}  // namespace
+
+namespace {
+// SOFTRAY_WAVE_TIMING=1: CUDA-event time of every stage, summed over the chunks of the frame, printed to stderr
+// (debugging aid: synchronises the stream at the end of the frame).
+struct StageTimer {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> stage;
+    void mark(int which)
+    {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+        ev.push_back(e); stage.push_back(which);
+    }
+    void report()
+    {
+        if (!on || ev.empty()) return;
+        static const char* names[] = {"begin", "search", "hit", "fallback", "search_ref", "hit_ref", "fallback_ref", "shadow", "shadow_fb", "compose"};
+        double sum[10] = {0};
+        cudaStreamSynchronize(st);
+        for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); sum[stage[i]] += ms; }
+        std::fprintf(stderr, "softray wave stages (ms):");
+        for (int k = 1; k < 10; k++) if (sum[k] > 0) std::fprintf(stderr, " %s %.3f", names[k], sum[k]);
+        std::fprintf(stderr, "\n");
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+};
+}  // namespace
+
+// One frame: every chunk of tiles through the stage kernels.  Everything is stream-ordered; nothing synchronises
+// the host.  Consecutive chunks alternate between two streams (each with its own set of buffers): while one chunk
+// sits in a stage with little parallelism (the fallback kernels: a few thousand rays with long serial walks; the
+// tail of any kernel), the other chunk's kernels fill the machine.
+cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets, const WaveBufs bufs[2],
                         uint32_t cap_samples, uint32_t* d_pixels, int32_t* d_ids, DevCounters* d_counters, int sm_count,
-                        cudaStream_t stream, int* launches)
+                        cudaStream_t stream, cudaStream_t side_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, int* launches)
 {
     const int nn = f.sub_pixel_res * f.sub_pixel_res;
     const uint32_t per_tile = 32u * (uint32_t)nn;
     const long long n_tiles = (long long)f.tiles_x * f.tiles_y;
-    const uint32_t tiles_per_chunk = cap_samples / per_tile;
-    if (tiles_per_chunk == 0) return cudaErrorInvalidValue;
+    if (cap_samples / per_tile == 0) return cudaErrorInvalidValue;
+    long long n_chunks = (n_tiles * per_tile + cap_samples - 1) / cap_samples;
+    const bool two = side_stream != nullptr && env_occ("SOFTRAY_WAVE_STREAMS", 2) >= 2 && n_tiles * per_tile >= (1u << 20);
+    if (two && n_chunks < 2) n_chunks = 2;
+    if (two && (n_chunks & 1)) n_chunks++;
+    const long long tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
     const int bounces = (f.reflection_depth > 0 && f.n_instances == 1) ? f.reflection_depth : 0;
     const size_t smem_shadow = sizeof(double) * 3 * (size_t)(f.shadows ? f.shadow_samples : 0);
-    if (smem_shadow > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shadow);
-        if (e != cudaSuccess) return e;
-    }
+    const int occ_search = env_occ("SOFTRAY_WAVE_SEARCH_OCC", 4), occ_hit = env_occ("SOFTRAY_WAVE_HIT_OCC", 3),
+              occ_shadow = env_occ("SOFTRAY_WAVE_SHADOW_OCC", 4);
     const int persistent = sm_count * 8;          // grid of the list kernels (grid-stride over a device-side count)
     int n_launch = 0;
-    for (long long tile0 = 0; tile0 < n_tiles; tile0 += tiles_per_chunk) {
+    StageTimer tm; tm.st = stream;
+    { const char* e = std::getenv("SOFTRAY_WAVE_TIMING"); tm.on = e && *e == '1' && !two; }
+    cudaError_t e;
+    if (two) {
+        if ((e = cudaEventRecord(ev_fork, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(side_stream, ev_fork, 0)) != cudaSuccess) return e;
+    }
+    int ci = 0;
+    for (long long tile0 = 0; tile0 < n_tiles; tile0 += tiles_per_chunk, ci++) {
+        cudaStream_t st = (two && (ci & 1)) ? side_stream : stream;
+        const WaveBufs& wb = bufs[(two && (ci & 1)) ? 1 : 0];
         WaveArgs a;
-        a.f = f; a.sc = sc; a.insts = d_insts; a.offsets = d_offsets; a.b = bufs; a.counters = d_counters;
+        a.f = f; a.sc = sc; a.insts = d_insts; a.offsets = d_offsets; a.b = wb; a.counters = d_counters;
         a.tile0 = (int)tile0;
-        a.n_tiles = (uint32_t)((n_tiles - tile0) < (long long)tiles_per_chunk ? (n_tiles - tile0) : (long long)tiles_per_chunk);
+        a.n_tiles = (uint32_t)((n_tiles - tile0) < tiles_per_chunk ? (n_tiles - tile0) : tiles_per_chunk);
         a.n_samples = a.n_tiles * per_tile;
         a.n_rays = a.n_samples;
         a.ref_in = 0; a.ref_out = 0; a.fb_slot = 0;
         a.cap_shadow_fallback = cap_samples;
-        cudaError_t e = cudaMemsetAsync(bufs.counts, 0, sizeof(WaveCounts), stream);
-        if (e != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(wb.counts, 0, sizeof(WaveCounts), st)) != cudaSuccess) return e;
         const int grid_cam = (int)((a.n_rays + kWaveThreads - 1) / kWaveThreads);
-        k_search<0><<<grid_cam, kWaveThreads, 0, stream>>>(a);
-        k_hit<0><<<grid_cam, kWaveThreads, 0, stream>>>(a);
-        k_fallback<0><<<sm_count, kWaveThreads, 0, stream>>>(a);
+        tm.mark(0);
+        launch_search<0>(occ_search, grid_cam, st, a); tm.mark(1);
+        launch_hit<0>(occ_hit, grid_cam, st, a); tm.mark(2);
+        k_fallback<0><<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(3);
         n_launch += 3;
         for (int depth = 1; depth <= bounces; depth++) {
             a.ref_in = (depth - 1) & 1; a.ref_out = depth & 1; a.fb_slot = depth;
             // (the list written two bounces ago is consumed: its counter restarts)
-            e = cudaMemsetAsync(&bufs.counts->n_ref[a.ref_out], 0, sizeof(uint32_t), stream);
-            if (e != cudaSuccess) return e;
-            k_search<1><<<persistent, kWaveThreads, 0, stream>>>(a);
-            k_hit<1><<<persistent, kWaveThreads, 0, stream>>>(a);
-            k_fallback<1><<<sm_count, kWaveThreads, 0, stream>>>(a);
+            if ((e = cudaMemsetAsync(&wb.counts->n_ref[a.ref_out], 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
+            launch_search<1>(occ_search, persistent, st, a); tm.mark(4);
+            launch_hit<1>(occ_hit, persistent, st, a); tm.mark(5);
+            k_fallback<1><<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(6);
             n_launch += 3;
         }
         if (f.shadows) {
-            k_shadow<<<persistent, kWaveThreads, smem_shadow, stream>>>(a);
-            k_shadow_fallback<<<sm_count, kWaveThreads, 0, stream>>>(a);
+            if ((e = launch_shadow(occ_shadow, sm_count * occ_shadow, smem_shadow, st, a)) != cudaSuccess) return e;
+            tm.mark(7);
+            k_shadow_fallback<<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(8);
             n_launch += 2;
         }
-        k_compose<<<(int)((a.n_tiles * 32u + kWaveThreads - 1) / kWaveThreads), kWaveThreads, 0, stream>>>(a, d_pixels, d_ids);
+        k_compose<<<(int)((a.n_tiles * 32u + kWaveThreads - 1) / kWaveThreads), kWaveThreads, 0, st>>>(a, d_pixels, d_ids);
         n_launch += 1;
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
+        tm.mark(9);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    if (two) {
+        if ((e = cudaEventRecord(ev_join, side_stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream, ev_join, 0)) != cudaSuccess) return e;
+    }
+    tm.report();
     if (launches) *launches = n_launch;
     return cudaSuccess;
 }

@@ -70,8 +70,8 @@ struct WaveArgs {
 
 size_t wave_buffer_bytes(uint32_t cap_samples, int depth_slots, WaveLayout* lay);
 void wave_bind(void* base, const WaveLayout& lay, WaveBufs* b);
-cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets, const WaveBufs& bufs,
+cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets, const WaveBufs bufs[2],
                         uint32_t cap_samples, uint32_t* d_pixels, int32_t* d_ids, DevCounters* d_counters, int sm_count,
-                        cudaStream_t stream, int* launches);
+                        cudaStream_t stream, cudaStream_t side_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, int* launches);
 
 }  // namespace sr

@@ -14,7 +14,7 @@ from . import abi
 from .scene import FrameParams, MeshData, SceneDescHolder, SphereData
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsoftray_cuda.so")
+SO_PATH = os.environ.get("SOFTRAY_SO") or os.path.join(_HERE, "libsoftray_cuda.so")   # SOFTRAY_SO: an experimental build (scripts/build_variant.py)
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["sr_api.cu", "sr_render.cu", "sr_diag.cu", "sr_bvh.cpp", "sr_model3ds.cpp", "sr_resolve.cu", "sr_lbvh.cu", "sr_wave.cu"]
 HEADERS = ["sr_types.h", "sr_bvh.h", "sr_device.cuh", "sr_wave.h", os.path.join("..", "..", "include", "softray_cuda.h")]
