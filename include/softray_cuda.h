@@ -173,8 +173,23 @@ typedef struct softray_frame {
      * SOFTRAY_FILTER_VERIFY  both on every ray, contradictions counted in
      * softray_stats.filter_mismatch (must stay 0). */
     int32_t filter_mode;
-    int32_t _reserved[3];
+    /* != 0: time every stage kernel of the frame with CUDA events (softray_stats.ms_stage; needs stats != NULL).
+     * The stage-kernel pipeline then runs its chunks one after the other instead of two at a time, so the
+     * frame itself is slower: a measuring aid (bench.py's per-kernel roofline), off by default. */
+    int32_t profile_stages;
+    int32_t _reserved[2];
 } softray_frame;
+
+#define SOFTRAY_N_STAGES 10
+#define SOFTRAY_STAGE_SEARCH        0   /* camera rays: ray generation + FP32 filtered closest-hit search        */
+#define SOFTRAY_STAGE_HIT           1   /* camera rays: candidates through the reference arithmetic + shading    */
+#define SOFTRAY_STAGE_FALLBACK      2   /* camera rays the search could not bracket: full exact walk             */
+#define SOFTRAY_STAGE_SEARCH_REF    3   /* the same three for the reflection rays (all bounces)                  */
+#define SOFTRAY_STAGE_HIT_REF       4
+#define SOFTRAY_STAGE_FALLBACK_REF  5
+#define SOFTRAY_STAGE_SHADOW        6   /* ShadowMethod rays (cone tests + filtered any-hit walks)               */
+#define SOFTRAY_STAGE_SHADOW_FB     7   /* shadow rays the filter could not decide                               */
+#define SOFTRAY_STAGE_COMPOSE       8   /* shadow byte, mirror blend, sub-pixel sums, pixel store                */
 
 #define SOFTRAY_FILTER_AUTO   0
 #define SOFTRAY_FILTER_OFF    1
@@ -204,6 +219,9 @@ typedef struct softray_stats {
     double   ms_h2d;           /* frame constants upload                                           */
     double   ms_d2h;           /* framebuffer (+hit ids) readback                                  */
     double   ms_total;         /* host wall time of the call                                       */
+    /* softray_frame.profile_stages: CUDA-event time of each stage of the stage-kernel pipeline, summed over the
+     * chunks of the frame (0 when not profiled, or when the frame ran the fused kernel: see `launches`) */
+    double   ms_stage[SOFTRAY_N_STAGES];
 } softray_stats;
 
 /* Host-buffer entry point: the drop-in for the body of Renderer.RaytraceGeometry.

@@ -25,6 +25,8 @@ FILTER_AUTO = 0
 FILTER_OFF = 1
 FILTER_VERIFY = 2
 
+STAGE_NAMES = ["search", "hit", "fallback", "search_ref", "hit_ref", "fallback_ref", "shadow", "shadow_fb", "compose"]
+
 ERROR_NAMES = {
     OK: "SOFTRAY_OK",
     E_INVALID_ARG: "SOFTRAY_E_INVALID_ARG",
@@ -117,7 +119,8 @@ class Frame(C.Structure):
         ("band_count", C.c_int32),
         ("band_index", C.c_int32),
         ("filter_mode", C.c_int32),
-        ("_reserved", C.c_int32 * 3),
+        ("profile_stages", C.c_int32),
+        ("_reserved", C.c_int32 * 2),
     ]
 
 
@@ -141,17 +144,23 @@ class Stats(C.Structure):
         ("ms_h2d", C.c_double),
         ("ms_d2h", C.c_double),
         ("ms_total", C.c_double),
+        ("ms_stage", C.c_double * 10),
     ]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        return {name: (list(getattr(self, name)) if name == "ms_stage" else getattr(self, name)) for name, _ in self._fields_}
+
+    @property
+    def stages(self):
+        """ms per stage of a frame rendered with profile_stages (empty for the fused kernel)."""
+        return {n: self.ms_stage[i] for i, n in enumerate(STAGE_NAMES) if self.ms_stage[i] > 0.0}
 
     @property
     def rays(self):
         return self.rays_primary + self.rays_shadow + self.rays_secondary
 
 
-EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 192, "stats": 144}
+EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 192, "stats": 224}
 
 assert C.sizeof(Mesh) == EXPECTED_SIZES["mesh"]
 assert C.sizeof(Sphere) == EXPECTED_SIZES["sphere"]

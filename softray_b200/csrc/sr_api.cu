@@ -87,6 +87,7 @@ struct softray_ctx {
     WaveBufs wave[2];                           // two chunks in flight (wave_render)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    StageTimer stage_timer;                     // softray_frame.profile_stages
     std::string err;
 };
 
@@ -763,6 +764,7 @@ struct Prepared {
     int grid = 0;
     size_t smem = 0;
     int start_row = 0, end_row = -1;
+    bool profile = false;              // softray_frame.profile_stages
     bool wave = false;                 // stage kernels (sr_wave.cu) instead of the fused kernel
     bool empty = false;                // no row to trace (start_row > end_row after the clamp): nothing is launched
 };
@@ -975,6 +977,7 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
         if (e && !std::strcmp(e, "fused")) want = false;
         if (e && !std::strcmp(e, "wave")) want = true;
         p->wave = capable && want;
+        p->profile = fr->profile_stages != 0;
     }
     return SOFTRAY_OK;
 }
@@ -1036,8 +1039,10 @@ int enqueue_frame(softray_ctx* ctx, const softray_scene* scene, const Prepared& 
             ctx->wave_bytes = 2 * bytes; ctx->wave_cap = new_cap; ctx->wave_slots = new_slots;
         }
         int launches = 0;
+        ctx->stage_timer.on = timed && p.profile;
         SR_CUDA(ctx, wave_render(f, scene->dev, ctx->d_insts, ctx->d_offsets, ctx->wave, (uint32_t)cap, d_pixels, d_ids, ctx->d_counters,
-                                 ctx->sm_count, stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join, &launches));
+                                 ctx->sm_count, stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join, &launches,
+                                 (timed && p.profile) ? &ctx->stage_timer : nullptr));
         ctx->last_launches = launches;
     } else
     SR_CUDA(ctx, launch_render(f, scene->dev, ctx->d_insts, ctx->d_offsets, d_pixels, d_ids, ctx->d_tile_counter,
@@ -1060,6 +1065,7 @@ int collect_stats(softray_ctx* ctx, cudaStream_t stream, softray_stats* st, bool
     st->filter_tests = c.filter_tests; st->filter_unsure = c.filter_unsure; st->filter_mismatch = c.filter_mismatch;
     st->rays_bundled = c.rays_bundled; st->rays_fallback = c.rays_fallback;
     st->launches = (uint64_t)ctx->last_launches;
+    if (ctx->stage_timer.on) { ctx->stage_timer.collect(st->ms_stage, SOFTRAY_N_STAGES); ctx->stage_timer.on = false; }
     float ms = 0.f;
     SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); st->ms_h2d = ms;
     SR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); st->ms_kernel = ms;

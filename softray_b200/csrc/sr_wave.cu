@@ -26,9 +26,7 @@
 #include "sr_device.cuh"
 #include "sr_wave.h"
 
-#include <cstdio>
 #include <cstdlib>
-#include <vector>
 
 namespace sr {
 
@@ -731,34 +729,24 @@ cudaError_t launch_shadow(int occ, int grid, size_t smem, cudaStream_t st, const
 }
 }  // namespace
 
-namespace {
-// SOFTRAY_WAVE_TIMING=1: CUDA-event time of every stage, summed over the chunks of the frame, printed to stderr
-// (debugging aid: synchronises the stream at the end of the frame).
-struct StageTimer {
-    bool on = false;
-    cudaStream_t st = nullptr;
-    std::vector<cudaEvent_t> ev;
-    std::vector<int> stage;
-    void mark(int which)
-    {
-        if (!on) return;
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
-        ev.push_back(e); stage.push_back(which);
+// softray_frame.profile_stages: an event after every stage kernel; wave_stage_times() turns them into ms per stage
+// once the stream has been synchronised.
+void StageTimer::mark(int which)
+{
+    if (!on) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+    ev.push_back(e); stage.push_back(which);
+}
+void StageTimer::collect(double* ms_stage, int n)
+{
+    for (int k = 0; k < n; k++) ms_stage[k] = 0.0;
+    for (size_t i = 1; i < ev.size(); i++) {
+        float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        if (stage[i] >= 0 && stage[i] < n) ms_stage[stage[i]] += ms;
     }
-    void report()
-    {
-        if (!on || ev.empty()) return;
-        static const char* names[] = {"begin", "search", "hit", "fallback", "search_ref", "hit_ref", "fallback_ref", "shadow", "shadow_fb", "compose"};
-        double sum[10] = {0};
-        cudaStreamSynchronize(st);
-        for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); sum[stage[i]] += ms; }
-        std::fprintf(stderr, "softray wave stages (ms):");
-        for (int k = 1; k < 10; k++) if (sum[k] > 0) std::fprintf(stderr, " %s %.3f", names[k], sum[k]);
-        std::fprintf(stderr, "\n");
-        for (cudaEvent_t e : ev) cudaEventDestroy(e);
-    }
-};
-}  // namespace
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear(); stage.clear();
+}
 
 // One frame: every chunk of tiles through the stage kernels.  Everything is stream-ordered; nothing synchronises
 // the host.  Consecutive chunks alternate between two streams (each with its own set of buffers): while one chunk
@@ -766,14 +754,16 @@ struct StageTimer {
 // tail of any kernel), the other chunk's kernels fill the machine.
 cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets, const WaveBufs bufs[2],
                         uint32_t cap_samples, uint32_t* d_pixels, int32_t* d_ids, DevCounters* d_counters, int sm_count,
-                        cudaStream_t stream, cudaStream_t side_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, int* launches)
+                        cudaStream_t stream, cudaStream_t side_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, int* launches,
+                        StageTimer* prof)
 {
     const int nn = f.sub_pixel_res * f.sub_pixel_res;
     const uint32_t per_tile = 32u * (uint32_t)nn;
     const long long n_tiles = (long long)f.tiles_x * f.tiles_y;
     if (cap_samples / per_tile == 0) return cudaErrorInvalidValue;
     long long n_chunks = (n_tiles * per_tile + cap_samples - 1) / cap_samples;
-    const bool two = side_stream != nullptr && env_occ("SOFTRAY_WAVE_STREAMS", 2) >= 2 && n_tiles * per_tile >= (1u << 20);
+    const bool profiling = prof != nullptr && prof->on;
+    const bool two = side_stream != nullptr && !profiling && env_occ("SOFTRAY_WAVE_STREAMS", 2) >= 2 && n_tiles * per_tile >= (1u << 20);
     if (two && n_chunks < 2) n_chunks = 2;
     if (two && (n_chunks & 1)) n_chunks++;
     const long long tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
@@ -783,8 +773,9 @@ cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance
               occ_shadow = env_occ("SOFTRAY_WAVE_SHADOW_OCC", 4);
     const int persistent = sm_count * 8;          // grid of the list kernels (grid-stride over a device-side count)
     int n_launch = 0;
-    StageTimer tm; tm.st = stream;
-    { const char* e = std::getenv("SOFTRAY_WAVE_TIMING"); tm.on = e && *e == '1' && !two; }
+    StageTimer none;
+    StageTimer& tm = profiling ? *prof : none;
+    tm.st = stream;
     cudaError_t e;
     if (two) {
         if ((e = cudaEventRecord(ev_fork, stream)) != cudaSuccess) return e;
@@ -804,36 +795,35 @@ cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance
         a.cap_shadow_fallback = cap_samples;
         if ((e = cudaMemsetAsync(wb.counts, 0, sizeof(WaveCounts), st)) != cudaSuccess) return e;
         const int grid_cam = (int)((a.n_rays + kWaveThreads - 1) / kWaveThreads);
-        tm.mark(0);
-        launch_search<0>(occ_search, grid_cam, st, a); tm.mark(1);
-        launch_hit<0>(occ_hit, grid_cam, st, a); tm.mark(2);
-        k_fallback<0><<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(3);
+        tm.mark(-1);
+        launch_search<0>(occ_search, grid_cam, st, a); tm.mark(0);
+        launch_hit<0>(occ_hit, grid_cam, st, a); tm.mark(1);
+        k_fallback<0><<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(2);
         n_launch += 3;
         for (int depth = 1; depth <= bounces; depth++) {
             a.ref_in = (depth - 1) & 1; a.ref_out = depth & 1; a.fb_slot = depth;
             // (the list written two bounces ago is consumed: its counter restarts)
             if ((e = cudaMemsetAsync(&wb.counts->n_ref[a.ref_out], 0, sizeof(uint32_t), st)) != cudaSuccess) return e;
-            launch_search<1>(occ_search, persistent, st, a); tm.mark(4);
-            launch_hit<1>(occ_hit, persistent, st, a); tm.mark(5);
-            k_fallback<1><<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(6);
+            launch_search<1>(occ_search, persistent, st, a); tm.mark(3);
+            launch_hit<1>(occ_hit, persistent, st, a); tm.mark(4);
+            k_fallback<1><<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(5);
             n_launch += 3;
         }
         if (f.shadows) {
             if ((e = launch_shadow(occ_shadow, sm_count * occ_shadow, smem_shadow, st, a)) != cudaSuccess) return e;
-            tm.mark(7);
-            k_shadow_fallback<<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(8);
+            tm.mark(6);
+            k_shadow_fallback<<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(7);
             n_launch += 2;
         }
         k_compose<<<(int)((a.n_tiles * 32u + kWaveThreads - 1) / kWaveThreads), kWaveThreads, 0, st>>>(a, d_pixels, d_ids);
         n_launch += 1;
-        tm.mark(9);
+        tm.mark(8);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (two) {
         if ((e = cudaEventRecord(ev_join, side_stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(stream, ev_join, 0)) != cudaSuccess) return e;
     }
-    tm.report();
     if (launches) *launches = n_launch;
     return cudaSuccess;
 }

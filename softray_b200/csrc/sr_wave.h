@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "sr_types.h"
 
 namespace sr {
@@ -68,10 +70,20 @@ struct WaveArgs {
     int ref_in, ref_out, fb_slot;
 };
 
+struct StageTimer {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> stage;
+    void mark(int which);                       // an event now; the time since the previous mark is charged to `which`
+    void collect(double* ms_stage, int n);      // after the stream has been synchronised
+};
+
 size_t wave_buffer_bytes(uint32_t cap_samples, int depth_slots, WaveLayout* lay);
 void wave_bind(void* base, const WaveLayout& lay, WaveBufs* b);
 cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets, const WaveBufs bufs[2],
                         uint32_t cap_samples, uint32_t* d_pixels, int32_t* d_ids, DevCounters* d_counters, int sm_count,
-                        cudaStream_t stream, cudaStream_t side_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, int* launches);
+                        cudaStream_t stream, cudaStream_t side_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, int* launches,
+                        StageTimer* prof);
 
 }  // namespace sr

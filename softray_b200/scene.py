@@ -145,6 +145,7 @@ class FrameParams:
     band_count: int = 1
     band_index: int = 0
     filter_mode: int = 0  # abi.FILTER_AUTO / FILTER_OFF / FILTER_VERIFY (results identical in every mode)
+    profile_stages: bool = False  # time every stage kernel (softray_stats.ms_stage); a measuring aid
 
     def default_light(self):
         inv = 1.0 / math.sqrt((-1.0) * (-1.0) + (-1.0) * (-1.0) + 1.0 * 1.0)  # Vector.Normalise
@@ -191,5 +192,6 @@ class FrameParams:
         f.band_count = self.band_count
         f.band_index = self.band_index
         f.filter_mode = self.filter_mode
+        f.profile_stages = int(bool(self.profile_stages))
         f._keepalive = inst
         return f
