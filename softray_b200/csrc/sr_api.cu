@@ -828,6 +828,8 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     for (int k = 0; k < 3; k++) { f.light_dir_view[k] = fr->light_dir_view[k]; f.light_pos_view[k] = fr->light_pos_view[k]; }
     f.fov_depth = fr->fov_depth; f.focal_depth = fr->focal_depth; f.focal_strength = fr->focal_strength;
     f.aspect = (double)fr->height / (double)fr->width;                 // Renderer.cs:621
+    // shade(): largest |cos| whose shininess-th power is surely below 2^-82 (0: never skip)
+    f.spec_skip = (fr->shininess >= 1.0 && std::isfinite(fr->shininess)) ? std::exp2(-82.0 / fr->shininess) * (1.0 - 1e-9) : 0.0;
     f.width = fr->width; f.height = fr->height;
     // clamp rows like Renderer.cs:1652-1653
     int s = fr->start_row < 0 ? 0 : fr->start_row; if (s > fr->height - 1) s = fr->height - 1;

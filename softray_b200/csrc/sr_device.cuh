@@ -1272,13 +1272,19 @@ __device__ __forceinline__ uint32_t shade(const DevFrame& f, const DevInstance& 
     const double ldn = vdot(to_light, nv);
     const double diffuse = fmax(0.0, ldn);
     double specular = 0.0;
-    if (f.specular_lighting) {
+    const double amb_diff = dadd(f.ambient, diffuse);
+    // ambient + diffuse >= 1: min(1, . + specular) is 1 whatever the (non-negative) specular term is
+    if (f.specular_lighting && amb_diff < 1.0) {
         const d3 to_cam = vnormalise(vneg(v));
         const d3 refl = vsub(vscale(nv, dmul(2.0, ldn)), to_light);
         const double cos_a = vdot(refl, to_cam);
-        specular = fmax(0.0, pow(cos_a, f.shininess));     // Math.Pow then Math.Max (:153-154)
+        // Math.Pow then Math.Max (:153-154).  |pow(c, s)| <= |c|^s (or the result is NaN / negative and Max makes it 0):
+        // below spec_skip = 2^(-82/s) it is < 2^-82, less than half an ulp of any ambient + diffuse >= 2^-20, so adding
+        // it returns ambient + diffuse bit for bit -- the ~300-instruction FP64 pow is only run where it can matter
+        if (!(fabs(cos_a) < f.spec_skip && amb_diff >= 9.5367431640625e-07))
+            specular = fmax(0.0, pow(cos_a, f.shininess));
     }
-    double ch = dadd(dadd(f.ambient, diffuse), specular);   // white material, (a + d) + s
+    double ch = dadd(amb_diff, specular);                   // white material, (a + d) + s
     ch = fmin(ch, 1.0);
     return modulate(color, to_byte(dmul(255.0, ch)));
 }

@@ -116,6 +116,7 @@ struct DevFrame {
     double ambient, shininess;
     double light_dir_view[3], light_pos_view[3];
     double fov_depth, focal_depth, focal_strength, aspect;
+    double spec_skip;           // |R.cam| below this: pow(R.cam, shininess) < 2^-82 cannot change ambient + diffuse (shade())
     int32_t width, height, start_row, end_row;
     int32_t sub_pixel_res, focal_blur, subdivision, shading;
     int32_t shadows, shadow_samples, point_lighting, specular_lighting;

@@ -417,49 +417,99 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_hit(const __grid_constan
     flush_counters(a.counters, v);
 }
 
-// The rays of the fallback list through the full reference-arithmetic search (closest_hit with the filter off:
-// exact BVH walk behind the full root-box clip), then the same continuation.
+// The rays of the fallback list through the full reference-arithmetic search: SpatialSubdivision.IntersectRay's
+// root-box clip (reference_clip), then every triangle whose (FP32, padded) leaf box the ray touches through
+// Triangle.IntersectRay, nearest rayFrac wins, ties to the lowest triangle index / lowest instance -- the result of
+// mesh_closest_exact's full walk.  These rays are few (thousands per frame) but their walks are long (a ray through
+// the pole of a lat-long sphere meets hundreds of sliver triangles), so ONE WARP takes one ray: the walk is uniform
+// over the warp (every node fetch is a broadcast), leaf triangles are collected 32 at a time and tested by the 32
+// lanes side by side, a lexicographic warp reduction keeps the winner.  (Per-lane rays left the kernel at the mercy
+// of its slowest thread: 15 ms per config4 frame for 1 178 rays.)
+struct WarpBest { double rf; int index; int k; };
+
+__device__ __forceinline__ void fallback_flush(const TriRec* __restrict__ tris, const int* list, int n, d3 ts, d3 dir, WarpBest& best,
+                                               unsigned int* n_tests)
+{
+    const int lane = (int)lane_id();
+    double rf = kNoHit; int index = 0x7fffffff, k = -1;
+    __syncwarp();
+    if (lane < n) {
+        const int kk = list[lane];
+        double r;
+        (*n_tests)++;
+        if (tri_intersect(tris + kk, ts, dir, best.rf, &r)) { rf = r; k = kk; index = __ldg(reinterpret_cast<const int*>(tris + kk) + 31); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double orf = __shfl_xor_sync(0xffffffffu, rf, o);
+        const int oidx = __shfl_xor_sync(0xffffffffu, index, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, k, o);
+        if (orf < rf || (orf == rf && oidx < index)) { rf = orf; index = oidx; k = ok; }
+    }
+    if (k >= 0 && (rf < best.rf || (rf == best.rf && index < best.index))) { best.rf = rf; best.index = index; best.k = k; }
+    __syncwarp();
+}
+
 template <int SRC>
 __global__ void __launch_bounds__(kWaveThreads) k_fallback(const __grid_constant__ WaveArgs a)
 {
     const DevFrame& f = a.f;
     const DevInstance* __restrict__ insts = a.insts;
+    __shared__ int s_list[kWaveThreads / 32][32];
+    int* list = s_list[threadIdx.x >> 5];
     int walk_stack[kStackEntries];
-    XCounters xc; xc.stack = walk_stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0;
-    xc.filter_unsure = 0; xc.filter_mismatch = 0;
-    unsigned int n_shadow = 0, n_secondary = 0, n_hits = 0, n_shaded = 0;
+    unsigned int n_nodes = 0, n_tests = 0, n_shadow = 0, n_secondary = 0, n_hits = 0, n_shaded = 0;
     const uint32_t n = __ldg(&a.b.counts->n_fallback[a.fb_slot]);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t q = base + lane_id();
-        const bool active = q < n;
-        d3 s = mk(0, 0, 0), dir = mk(0, 0, 0); uint32_t sample = 0, depth = 0;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += n_warps) {
+        d3 s, dir; uint32_t sample, depth;
+        const uint32_t r = a.b.fallback[q];
+        batch_ray<SRC>(a, insts, r, &s, &dir, &sample, &depth);
         ExactHit eh; eh.hit = false; eh.inst = 0; eh.k = -1; eh.index = 0x7fffffff; eh.rf = kNoHit; eh.rf_from_clip = 0.0;
         eh.clipped_start = s; eh.dir = dir;
-        if (active) {
-            const uint32_t r = a.b.fallback[q];
-            batch_ray<SRC>(a, insts, r, &s, &dir, &sample, &depth);
-            eh.dir = dir;
-            for (int i = 0; i < f.n_instances; i++) {
-                const DevInstance& in = insts[i];
-                const DevMesh& m = a.sc.meshes[in.mesh];
-                const d3 si = f.n_instances == 1 ? s : mk(in.start[0], in.start[1], in.start[2]);
-                const d3 di = f.n_instances == 1 ? dir : mul3x3(in.Minv, dir);
-                BestPrim bt; bt.rf = kNoHit; bt.k = -1; bt.index = 0x7fffffff;
-                d3 ts; double offset;
-                if (m.n_tris <= 0) continue;
-                mesh_closest_exact(m, f.subdivision, si, di, nullptr, 0, &bt, &ts, &offset, &xc);
-                if (bt.k < 0) continue;
-                const double rf = dadd(bt.rf, offset);
-                if (rf < eh.rf) {                                                 // strict: the lowest instance keeps a tie
-                    eh.hit = true; eh.inst = i; eh.k = bt.k; eh.index = bt.index; eh.rf_from_clip = bt.rf; eh.rf = rf;
-                    eh.clipped_start = ts; eh.dir = di;
-                }
+        for (int i = 0; i < f.n_instances; i++) {
+            const DevInstance& in = insts[i];
+            const DevMesh& m = a.sc.meshes[in.mesh];
+            if (m.n_tris <= 0) continue;
+            const d3 si = f.n_instances == 1 ? s : mk(in.start[0], in.start[1], in.start[2]);
+            const d3 di = f.n_instances == 1 ? dir : mul3x3(in.Minv, dir);
+            d3 ts = si; double offset = 0.0;
+            if (f.subdivision && !reference_clip(m.bmin, m.bmax, &ts, di, &offset)) continue;      // SpatialSubdivision.cs:389-398
+            double te = 0.0;
+            if (!f.subdivision && !entry_clip(m.bmin, m.bmax, 0.0, ts, di, &te)) continue;
+            const TravRay tr = make_trav(ts, di, te);
+            // rayFrac = rf + offset must beat the best of the earlier instances (strictly: the lowest instance keeps a tie)
+            WarpBest best; best.rf = eh.hit ? eh.rf - offset : kNoHit; best.index = 0x7fffffff; best.k = -1;
+            if (eh.hit) best.rf = best.rf * (1.0 + 1e-15) + 1e-300;                                 // (only a cull: the comparison below decides)
+            float tcull = cull_from(best.rf, tr.t_off);
+            int n_list = 0;
+            const unsigned int nv = walk_bvh(
+                m.nodes, m.n_tris, walk_stack,
+                [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float* t) {
+                    return slab(tr, lox, loy, loz, hix, hiy, hiz, tcull, t);
+                },
+                [&](int first, int count) {
+                    for (int j = 0; j < count; j++) {
+                        list[n_list++] = first + j;                                                 // (every lane stores the same value)
+                        if (n_list == 32) {
+                            fallback_flush(m.tris, list, n_list, ts, di, best, &n_tests);
+                            n_list = 0;
+                            tcull = cull_from(best.rf, tr.t_off);
+                        }
+                    }
+                    return false;
+                });
+            if (n_list > 0) fallback_flush(m.tris, list, n_list, ts, di, best, &n_tests);
+            if (lane_id() == 0) n_nodes += nv;
+            if (best.k < 0) continue;
+            const double rf = dadd(best.rf, offset);                                                // SpatialSubdivision.cs:416
+            if (rf < eh.rf) {
+                eh.hit = true; eh.inst = i; eh.k = best.k; eh.index = best.index; eh.rf_from_clip = best.rf; eh.rf = rf;
+                eh.clipped_start = ts; eh.dir = di;
             }
         }
-        spawn_from_hit<SRC>(a, insts, active, eh.hit, eh, sample, depth, &n_shaded, &n_shadow, &n_secondary, &n_hits);
+        spawn_from_hit<SRC>(a, insts, lane_id() == 0, eh.hit, eh, sample, depth, &n_shaded, &n_shadow, &n_secondary, &n_hits);
     }
-    const unsigned long long v[13] = {0, n_shadow, n_secondary, xc.node_visits, xc.prim_tests, 0, n_hits, n_shaded, 0, 0, 0, 0, 0};
+    const unsigned long long v[13] = {0, n_shadow, n_secondary, n_nodes, n_tests, 0, n_hits, n_shaded, 0, 0, 0, 0, 0};
     flush_counters(a.counters, v);
 }
 
