@@ -399,6 +399,18 @@ inline int env_int(const char* name, int dflt)
 constexpr int kLbvhLeaf = 1;
 inline int lbvh_leaf_max() { const int v = env_int("SOFTRAY_LBVH_LEAF", kLbvhLeaf); return v < 1 ? 1 : (v > kMaxLeafPrims ? kMaxLeafPrims : v); }
 
+inline FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f; f.d = d ? d : 1u; f._pad = 0; f.mul = 0; f.shift = 0;
+    if (f.d == 1u) return f;
+    uint32_t lg = 0;
+    while ((1ull << lg) < f.d) lg++;                       // ceil(log2 d)
+    const uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + f.d - 1) / f.d);
+    f.shift = p - 32;
+    return f;
+}
+
 inline float traversal_pad(double max_coord) { return round_up(std::ldexp(std::fmax(max_coord, 1e-30), -18)); }
 
 }  // namespace
@@ -953,6 +965,9 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     f.tiles_x = (f.width + 7) / 8;
     f.tiles_per_band = (f.band_height + 3) / 4;
     f.tiles_y = my_bands * f.tiles_per_band;
+    f.fd_n = make_fastdiv((uint32_t)f.sub_pixel_res); f.fd_nn = make_fastdiv((uint32_t)(f.sub_pixel_res * f.sub_pixel_res));
+    f.fd_per_tile = make_fastdiv(32u * (uint32_t)(f.sub_pixel_res * f.sub_pixel_res));
+    f.fd_tiles_x = make_fastdiv((uint32_t)f.tiles_x); f.fd_tiles_per_band = make_fastdiv((uint32_t)f.tiles_per_band);
     p->smem = sizeof(DevInstance) * (size_t)f.n_instances + sizeof(double) * 3 * (size_t)f.shadow_samples;
     int occ = render_kernel_occupancy((int)p->smem);
     if (occ < 1) occ = 1;

@@ -112,6 +112,15 @@ struct DevInstance {
     int32_t _pad;
 };
 
+// n / d for a divisor fixed per frame and n < 2^31: one multiply-high and a shift instead of the ~20-instruction
+// integer division (the stage kernels turn a ray index into tile / pixel / sub-pixel coordinates five divisions deep)
+struct FastDiv {
+    uint32_t mul, shift, d, _pad;
+#if defined(__CUDACC__)
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1u ? n : (__umulhi(n, mul) >> shift); }
+#endif
+};
+
 struct DevFrame {
     double ambient, shininess;
     double light_dir_view[3], light_pos_view[3];
@@ -127,6 +136,7 @@ struct DevFrame {
     // band_index + j * band_count, rows start_row + band * band_height ...; an unbanded frame is
     // one band of end_row - start_row + 1 rows
     int32_t band_height, band_count, band_index, tiles_per_band;
+    FastDiv fd_n, fd_nn, fd_per_tile, fd_tiles_x, fd_tiles_per_band;   // sub_pixel_res, its square, 32 * that, tiles_x, tiles_per_band
     int32_t filter_mode;        // SOFTRAY_FILTER_*: 0 filter + exact fallback, 1 exact only, 2 verify
     float   light_radius;       // >= the length of every area-light offset (0.2, ShadowMethod.cs:10), rounded up
     int32_t bundle_budget;      // node visits a shadow-bundle cone walk may spend before giving up (0 = no bundles)

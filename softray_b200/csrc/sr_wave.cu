@@ -48,13 +48,14 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool want)
     return base + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u));
 }
 
+// One atomic per warp per non-zero counter.  The per-thread counts are 32-bit (a thread sees a few thousand rays per
+// launch at most), so the warp sum is ONE redux instruction instead of ten shuffles.
 __device__ __forceinline__ void flush_counters(DevCounters* counters, const unsigned long long (&v)[13])
 {
 #pragma unroll
     for (int k = 0; k < 13; k++) {
-        unsigned long long x = v[k];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane_id() == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + k, x);
+        const unsigned int x = __reduce_add_sync(0xffffffffu, (unsigned int)v[k]);
+        if (lane_id() == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + k, (unsigned long long)x);
     }
 }
 
@@ -67,16 +68,16 @@ __device__ __forceinline__ bool camera_ray(const DevFrame& f, const DevInstance&
 {
     const int n = f.sub_pixel_res, nn = n * n;
     const int W = f.width, H = f.height;
-    const int ty = tile / f.tiles_x, tx = tile - ty * f.tiles_x;
-    const int band_j = ty / f.tiles_per_band;
+    const int ty = (int)f.fd_tiles_x.div((uint32_t)tile), tx = tile - ty * f.tiles_x;
+    const int band_j = (int)f.fd_tiles_per_band.div((uint32_t)ty);
     const int row0 = f.start_row + (f.band_index + band_j * f.band_count) * f.band_height;
     const int band_r0 = (ty - band_j * f.tiles_per_band) * 4;
-    const int px = w / nn, si = w - px * nn;
+    const int px = (int)f.fd_nn.div((uint32_t)w), si = w - px * nn;
     const int col = tx * 8 + (px & 7);
     const int band_r = band_r0 + (px >> 3);
     const int row = row0 + band_r;
     if (col >= W || band_r >= f.band_height || row > f.end_row) return false;
-    const int sx = si / n, sy = si - sx * n;                                      // subX outer, subY inner (:1762-1764)
+    const int sx = (int)f.fd_n.div((uint32_t)si), sy = si - sx * n;               // subX outer, subY inner (:1762-1764)
     double fx = 0.0, fy = 0.0;
     if (n > 1) {
         fx = dsub(ddiv((double)sx, (double)(n - 1)), 0.5);                        // :1767-1768
@@ -111,7 +112,7 @@ __device__ __forceinline__ bool batch_ray(const WaveArgs& a, const DevInstance* 
     if (SRC == 0) {
         const int nn = f.sub_pixel_res * f.sub_pixel_res;
         const int per_tile = 32 * nn;
-        const int t = (int)(r / (uint32_t)per_tile), w = (int)(r - (uint32_t)t * (uint32_t)per_tile);
+        const int t = (int)f.fd_per_tile.div(r), w = (int)(r - (uint32_t)t * (uint32_t)per_tile);
         bool is_view;
         *sample = r; *depth = 0;
         if (!camera_ray(f, insts[0], a.tile0 + t, w, start, dir, &is_view)) return false;
@@ -653,8 +654,8 @@ __global__ void __launch_bounds__(kWaveThreads) k_compose(const __grid_constant_
     if (p >= n_px) return;
     const int t = (int)(p >> 5), px = (int)(p & 31u);
     const int tile = a.tile0 + t;
-    const int ty = tile / f.tiles_x, tx = tile - ty * f.tiles_x;
-    const int band_j = ty / f.tiles_per_band;
+    const int ty = (int)f.fd_tiles_x.div((uint32_t)tile), tx = tile - ty * f.tiles_x;
+    const int band_j = (int)f.fd_tiles_per_band.div((uint32_t)ty);
     const int row0 = f.start_row + (f.band_index + band_j * f.band_count) * f.band_height;
     const int band_r = (ty - band_j * f.tiles_per_band) * 4 + (px >> 3);
     const int col = tx * 8 + (px & 7), row = row0 + band_r;
@@ -844,7 +845,9 @@ cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance
         a.ref_in = 0; a.ref_out = 0; a.fb_slot = 0;
         a.cap_shadow_fallback = cap_samples;
         if ((e = cudaMemsetAsync(wb.counts, 0, sizeof(WaveCounts), st)) != cudaSuccess) return e;
-        const int grid_cam = (int)((a.n_rays + kWaveThreads - 1) / kWaveThreads);
+        // (grid-stride loops: a thread takes several rays, the per-thread prologue / counter flush is paid once)
+        const int grid_need = (int)((a.n_rays + kWaveThreads - 1) / kWaveThreads);
+        const int grid_cam = grid_need < sm_count * 32 ? grid_need : sm_count * 32;
         tm.mark(-1);
         launch_search<0>(occ_search, grid_cam, st, a); tm.mark(0);
         launch_hit<0>(occ_hit, grid_cam, st, a); tm.mark(1);
