@@ -39,7 +39,7 @@ FLOPS = dict(primary=22, primary_aa=26, tri_test=41, tri_filter=11, sphere_test=
              shadow_setup=6, reflect_setup=14, texture=12)
 BYTES = dict(node=64, tri=128, tri_filter=64, sphere=48, pixel=4)   # what ONE visit / test / pixel has to move
 COUNTERS = ("rays_primary", "rays_shadow", "rays_secondary", "node_visits", "prim_tests", "sphere_tests", "hits_primary",
-            "shaded_hits", "filter_tests", "filter_unsure", "rays_bundled", "rays_fallback")
+            "shaded_hits", "filter_tests", "filter_unsure", "rays_bundled", "rays_fallback", "rays_short_listed")
 
 DESCRIPTIONS = {
     "config1": "configs[0]: Raytracer/obj.3DS (152 triangles) via the native 3DS loader, 512x512, 1 spp, primary rays + Lambert",

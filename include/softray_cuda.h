@@ -215,6 +215,8 @@ typedef struct softray_stats {
     uint64_t rays_fallback;    /* camera / reflection rays whose candidate search could not bracket the hit (more
                                   than 4 candidate triangles, an axis-parallel direction ...): answered by the
                                   full reference-arithmetic walk (stage-kernel pipeline only)               */
+    uint64_t rays_short_listed;/* of rays_shadow: tested against the <= 8 triangles the cone walk of their shading point
+                                  could not rule out, without a walk of their own (stage-kernel pipeline only)    */
     double   ms_kernel;        /* CUDA-event time of the render kernel(s)                          */
     double   ms_h2d;           /* frame constants upload                                           */
     double   ms_d2h;           /* framebuffer (+hit ids) readback                                  */

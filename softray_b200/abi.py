@@ -140,6 +140,7 @@ class Stats(C.Structure):
         ("filter_mismatch", C.c_uint64),
         ("rays_bundled", C.c_uint64),
         ("rays_fallback", C.c_uint64),
+        ("rays_short_listed", C.c_uint64),
         ("ms_kernel", C.c_double),
         ("ms_h2d", C.c_double),
         ("ms_d2h", C.c_double),
@@ -160,7 +161,7 @@ class Stats(C.Structure):
         return self.rays_primary + self.rays_shadow + self.rays_secondary
 
 
-EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 192, "stats": 224}
+EXPECTED_SIZES = {"mesh": 80, "sphere": 40, "scene_desc": 32, "instance": 288, "frame": 192, "stats": 232}
 
 assert C.sizeof(Mesh) == EXPECTED_SIZES["mesh"]
 assert C.sizeof(Sphere) == EXPECTED_SIZES["sphere"]

@@ -1080,7 +1080,7 @@ int collect_stats(softray_ctx* ctx, cudaStream_t stream, softray_stats* st, bool
     st->node_visits = c.node_visits; st->prim_tests = c.prim_tests; st->sphere_tests = c.sphere_tests;
     st->hits_primary = c.hits_primary; st->shaded_hits = c.shaded_hits;
     st->filter_tests = c.filter_tests; st->filter_unsure = c.filter_unsure; st->filter_mismatch = c.filter_mismatch;
-    st->rays_bundled = c.rays_bundled; st->rays_fallback = c.rays_fallback;
+    st->rays_bundled = c.rays_bundled; st->rays_fallback = c.rays_fallback; st->rays_short_listed = c.rays_short_listed;
     st->launches = (uint64_t)ctx->last_launches;
     if (ctx->stage_timer.on) { ctx->stage_timer.collect(st->ms_stage, SOFTRAY_N_STAGES); ctx->stage_timer.on = false; }
     float ms = 0.f;

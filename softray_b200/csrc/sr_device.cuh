@@ -1013,6 +1013,103 @@ __device__ __forceinline__ bool bundle_clear(const DevMesh& m, d3 end, d3 light,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shadow bundles with SUSPECTS (stage kernels).  bundle_clear above is all-or-nothing and its two-pass box test
+// grows every box by rho * (exit parameter): wide enough that on a dense mesh (config3: triangles of 0.001 under
+// a light of radius 0.2) the walk drowns in leaf boxes near the receiver and never succeeds.  Here:
+//  * the cone is tested against a box EXACTLY for its L-infinity hull: a point of a ray of the bundle at parameter
+//    tau is  o + (g_c + delta) tau  with |delta_k| <= rho, so on axis k it lies between o_k + (g_k - rho) tau and
+//    o_k + (g_k + rho) tau.  "Some point of the hull is inside [lo, hi] for some tau in [0, tcull]" is six linear
+//    inequalities in tau -- an interval intersection like the slab test, with slopes g_k -+ rho instead of g_k.
+//    A slope whose sign FP32 cannot vouch for drops its inequality (conservative).
+//  * the triangles no rule R1-R4 rejects are RETURNED (<= kMaxSuspects): the rays of the bundle then test only
+//    those, with the per-ray filter, and never walk.  Every other triangle is proven to be missed by every ray of
+//    the bundle in the reference arithmetic, so the answers are those of the per-ray walks.
+// Returns the number of suspects (0: every ray escapes), or -1: too many / out of budget (walk the rays).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxSuspects = 8;
+
+struct ConeAxes {
+    float ia[3], ib[3];       // 1 / (g_k + rho), 1 / (g_k - rho)
+    int sa[3], sb[3];         // sign of g_k + rho / g_k - rho: +1, -1, 0 = unknown (the inequality is dropped)
+};
+
+__device__ __forceinline__ bool cone_hull_slab(const FRay& r, const ConeAxes& ca, float lox, float loy, float loz, float hix, float hiy,
+                                               float hiz)
+{
+    const float lo[3] = {lox, loy, loz}, hi[3] = {hix, hiy, hiz}, o[3] = {r.ox, r.oy, r.oz};
+    float tmin = 0.0f, tmax = r.tcull;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float qa = (lo[k] - o[k]) * ca.ia[k];        // (g_k + rho) tau >= lo_k - o_k
+        const float qb = (hi[k] - o[k]) * ca.ib[k];        // (g_k - rho) tau <= hi_k - o_k
+        if (ca.sa[k] > 0) tmin = fmaxf(tmin, qa); else if (ca.sa[k] < 0) tmax = fminf(tmax, qa);
+        if (ca.sb[k] > 0) tmax = fminf(tmax, qb); else if (ca.sb[k] < 0) tmin = fmaxf(tmin, qb);
+    }
+    // the boxes are padded in space (sr_bvh.cpp), which covers the roundings above as it does for fslab
+    return tmin <= tmax;
+}
+
+__device__ __forceinline__ int bundle_suspects(const DevMesh& m, d3 end, d3 light, float rho, int budget, int* __restrict__ suspects,
+                                               Counters* c)
+{
+    FRay r;
+    r.ox = __double2float_rn(end.x); r.oy = __double2float_rn(end.y); r.oz = __double2float_rn(end.z);
+    r.gx = __double2float_rn(light.x - end.x); r.gy = __double2float_rn(light.y - end.y); r.gz = __double2float_rn(light.z - end.z);
+    const float agx = fabsf(r.gx), agy = fabsf(r.gy), agz = fabsf(r.gz);
+    const float aox = fabsf(r.ox), aoy = fabsf(r.oy), aoz = fabsf(r.oz);
+    r.g1 = agx + agy + agz; r.ginf = fmaxf(agx, fmaxf(agy, agz));
+    r.o1 = aox + aoy + aoz; r.oinf = fmaxf(aox, fmaxf(aoy, aoz));
+    if (!(r.ginf < 1e30f) || !(r.ginf > 1e-30f) || !(r.oinf <= 2.0f * m.scale)) return -1;
+    r.ix = r.iy = r.iz = 0.0f; r.nox = r.noy = r.noz = 0.0f;       // (the hull test has its own reciprocals)
+    r.tmin_hi = 0.0f; r.tmax_hi = 1.0f; r.tmax_lo = 1.0f; r.tcull = 1.00002f;
+    // the centre g_c itself is rounded: widen the ball by that much
+    const float rho_w = rho * (1.0f + 1e-5f) + (4.0f * kU) * r.ginf;
+    const float glen = sqrtf(r.gx * r.gx + r.gy * r.gy + r.gz * r.gz) * (1.0f + 8.0f * kU);
+    ConeAxes ca;
+    {
+        const float g[3] = {r.gx, r.gy, r.gz};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float a = g[k] + rho_w, b = g[k] - rho_w;
+            const float eps = (16.0f * kU) * (fabsf(g[k]) + rho_w) + 1e-30f;
+            ca.sa[k] = a > eps ? 1 : (a < -eps ? -1 : 0);
+            ca.sb[k] = b > eps ? 1 : (b < -eps ? -1 : 0);
+            ca.ia[k] = ca.sa[k] ? __fdiv_rn(1.0f, a) : 0.0f;
+            ca.ib[k] = ca.sb[k] ? __fdiv_rn(1.0f, b) : 0.0f;
+        }
+    }
+    int n = 0;
+    int s0 = -1, s1 = -1, s2 = -1, s3 = -1, s4 = -1, s5 = -1, s6 = -1, s7 = -1;
+    bool give_up = false;
+    unsigned int nf = 0;
+    c->node_visits += walk_bvh(
+        m.nodes, m.n_tris, c->stack,
+        [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float* t) {
+            *t = 0.0f;                                      // (no front-to-back order needed: every leaf is looked at)
+            if (--budget < 0) give_up = true;               // much geometry near the cone: trace the rays
+            return !give_up && cone_hull_slab(r, ca, lox, loy, loz, hix, hiy, hiz);
+        },
+        [&](int first, int count) {
+            for (int i = 0; i < count; i++) {
+                nf++;
+                if (tri_cone_reject(m.filt + first + i, r, rho_w, glen, m.scale)) continue;
+                const int k = first + i;
+                switch (n) {
+                case 0: s0 = k; break; case 1: s1 = k; break; case 2: s2 = k; break; case 3: s3 = k; break;
+                case 4: s4 = k; break; case 5: s5 = k; break; case 6: s6 = k; break; case 7: s7 = k; break;
+                default: give_up = true; return true;
+                }
+                n++;
+            }
+            return false;
+        });
+    c->filter_tests += nf;
+    if (give_up) return -1;
+    suspects[0] = s0; suspects[1] = s1; suspects[2] = s2; suspects[3] = s3; suspects[4] = s4; suspects[5] = s5; suspects[6] = s6; suspects[7] = s7;
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
 // rootGeometry: [ExtraGeometry spheres..., mesh through SpatialSubdivision | GeometryCollection]
 // ---------------------------------------------------------------------------------------------
 struct Hit {

@@ -149,7 +149,7 @@ struct DevFrame {
 
 struct DevCounters {            // summed over the launch with one atomic per warp per counter
     unsigned long long rays_primary, rays_shadow, rays_secondary, node_visits, prim_tests,
-        sphere_tests, hits_primary, shaded_hits, filter_tests, filter_unsure, filter_mismatch, rays_bundled, rays_fallback;
+        sphere_tests, hits_primary, shaded_hits, filter_tests, filter_unsure, filter_mismatch, rays_bundled, rays_fallback, rays_short_listed;
 };
 
 }  // namespace sr

@@ -50,10 +50,10 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool want)
 
 // One atomic per warp per non-zero counter.  The per-thread counts are 32-bit (a thread sees a few thousand rays per
 // launch at most), so the warp sum is ONE redux instruction instead of ten shuffles.
-__device__ __forceinline__ void flush_counters(DevCounters* counters, const unsigned long long (&v)[13])
+__device__ __forceinline__ void flush_counters(DevCounters* counters, const unsigned long long (&v)[14])
 {
 #pragma unroll
-    for (int k = 0; k < 13; k++) {
+    for (int k = 0; k < 14; k++) {
         const unsigned int x = __reduce_add_sync(0xffffffffu, (unsigned int)v[k]);
         if (lane_id() == 0 && x) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + k, (unsigned long long)x);
     }
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_search(const __grid_cons
         a.b.cand[r] = cand;
         a.b.meta[r] = state | insts_of;
     }
-    const unsigned long long v[13] = {0, 0, 0, xc.node_visits, 0, 0, 0, 0, xc.filter_tests, 0, 0, 0, 0};
+    const unsigned long long v[14] = {0, 0, 0, xc.node_visits, 0, 0, 0, 0, xc.filter_tests, 0, 0, 0, 0, 0};
     flush_counters(a.counters, v);
 }
 
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_hit(const __grid_constan
         }
         spawn_from_hit<SRC>(a, insts, active && !undecided, eh.hit, eh, sample, depth, &n_shaded, &n_shadow, &n_secondary, &n_hits);
     }
-    const unsigned long long v[13] = {n_primary, n_shadow, n_secondary, xc.node_visits, xc.prim_tests, 0, n_hits, n_shaded, 0, xc.filter_unsure, 0, 0, n_undecided};
+    const unsigned long long v[14] = {n_primary, n_shadow, n_secondary, xc.node_visits, xc.prim_tests, 0, n_hits, n_shaded, 0, xc.filter_unsure, 0, 0, n_undecided, 0};
     flush_counters(a.counters, v);
 }
 
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_fallback(const __grid_constant
         }
         spawn_from_hit<SRC>(a, insts, lane_id() == 0, eh.hit, eh, sample, depth, &n_shaded, &n_shadow, &n_secondary, &n_hits);
     }
-    const unsigned long long v[13] = {0, n_shadow, n_secondary, n_nodes, n_tests, 0, n_hits, n_shaded, 0, 0, 0, 0, 0};
+    const unsigned long long v[14] = {0, n_shadow, n_secondary, n_nodes, n_tests, 0, n_hits, n_shaded, 0, 0, 0, 0, 0, 0};
     flush_counters(a.counters, v);
 }
 
@@ -534,6 +534,7 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_cons
     c.filter_mismatch = 0; c.bundled = 0; c.bundle_skip = 0; c.stack = walk_stack;
     const uint32_t n_items = __ldg(&a.b.counts->n_shadow);
     const int n = f.shadow_samples;
+    unsigned int n_listed = 0;
     // a warp takes 32 consecutive shading points (neighbouring pixels: their rays towards sample i of the light run
     // side by side) and walks the n samples with them; warps fetch their groups from a queue
     for (;;) {
@@ -554,20 +555,24 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_cons
         const DevInstance& in = insts[inst];
         const DevMesh& m = a.sc.meshes[in.mesh];
         int escaped = 0;
-        bool all_clear = false;
+        // one conservative walk of the cone of this point's rays (bundle_suspects): 0 suspects = every ray escapes,
+        // 1..8 = the rays test those triangles only, -1 = the rays walk.  The block keeps the score of the cone
+        // walks (shade_and_shadow in sr_render.cu): where they keep failing, most points stop trying.
+        int suspects[kMaxSuspects];
+        int n_sus = -1;
         if (active && f.point_lighting && f.bundle_budget > 0) {
-            // (the block keeps the score of the cone walks: shade_and_shadow in sr_render.cu)
             const unsigned int ok = s_bundle_score[0], bad = s_bundle_score[1];
             c.bundle_skip++;
-            if (bad < 64u || ok * 32u >= bad || (c.bundle_skip & 255) == 0) {
+            if (bad < 64u || ok * 8u >= bad || (c.bundle_skip & 63) == 0) {
                 const d3 light = mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]);
-                all_clear = bundle_clear(m, end, light, f.light_radius, f.bundle_budget, &c);
-                if (all_clear) c.bundled += (unsigned int)n;
-                atomicAdd(&s_bundle_score[all_clear ? 0 : 1], 1u);
+                n_sus = bundle_suspects(m, end, light, f.light_radius, f.bundle_budget, suspects, &c);
+                if (n_sus == 0) c.bundled += (unsigned int)n;
+                if (n_sus > 0) n_listed += (unsigned int)n;
+                atomicAdd(&s_bundle_score[n_sus >= 0 ? 0 : 1], 1u);
             }
         }
-        if (all_clear) escaped = n;
-        const bool walk_rays = active && !all_clear;
+        if (n_sus == 0) escaped = n;
+        const bool walk_rays = active && n_sus != 0;
         for (int i = 0; i < n; i++) {
             bool unsure = false;
             ShadowFallback fb;
@@ -578,7 +583,27 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_cons
                 FRay r;
                 int list[kMaxCand] = {-1, -1, -1, -1}; int n_list = 0;
                 int res = fray_setup(m, f.subdivision, anchor, dir, &r);
-                if (res == 1) res = walk_filter_any(m.nodes, m.filt, m.n_tris, r, m.scale, list, &n_list, &c);
+                if (res == 1) {
+                    if (n_sus > 0) {
+                        // walk_filter_any's leaf test over the suspects: every other triangle is proven missed
+                        bool hit = false;
+                        unsigned int nf = 0;
+#pragma unroll
+                        for (int j = 0; j < kMaxSuspects; j++) {
+                            if (j < n_sus && !hit) {
+                                float tau, etau;
+                                nf++;
+                                const int t = tri_filter<false>(m.filt + suspects[j], r, m.scale, r.tmax_hi, &tau, &etau);
+                                if (t == 1) hit = true;
+                                else if (t == 2) { if (n_list < kMaxCand) list[n_list] = suspects[j]; n_list++; }
+                            }
+                        }
+                        c.filter_tests += nf;
+                        res = hit ? 1 : (n_list ? 2 : 0);
+                    } else {
+                        res = walk_filter_any(m.nodes, m.filt, m.n_tris, r, m.scale, list, &n_list, &c);
+                    }
+                }
                 if (res == 2) {
                     // the reference arithmetic looks at the triangles the filter could not decide (all of them when
                     // they are too many to list): shadow_fallback
@@ -612,7 +637,7 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_cons
         }
         if (active) a.b.slot_escaped[slot] = (uint32_t)escaped;
     }
-    const unsigned long long v[13] = {0, 0, 0, c.node_visits, c.prim_tests, 0, 0, 0, c.filter_tests, c.filter_unsure, 0, c.bundled, 0};
+    const unsigned long long v[14] = {0, 0, 0, c.node_visits, c.prim_tests, 0, 0, 0, c.filter_tests, c.filter_unsure, 0, c.bundled, 0, n_listed};
     flush_counters(a.counters, v);
 }
 
@@ -636,7 +661,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_shadow_fallback(const __grid_c
         const bool occ = occluded_mesh(m, f.subdivision, start, dir, n_list ? list : nullptr, n_list, &xc);
         if (!occ) atomicAdd(&a.b.slot_escaped[it.slot], 1u);
     }
-    const unsigned long long v[13] = {0, 0, 0, xc.node_visits, xc.prim_tests, 0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned long long v[14] = {0, 0, 0, xc.node_visits, xc.prim_tests, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     flush_counters(a.counters, v);
 }
 
