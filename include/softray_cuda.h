@@ -61,6 +61,17 @@ int  softray_create(int32_t device_ordinal, softray_ctx** out);
 void softray_destroy(softray_ctx* ctx);   /* also releases the scenes the context still owns; a handle that
                                             is not live (NULL, already destroyed) is ignored -- finalisers may
                                             run in any order (Renderer.Dispose vs the .NET finaliser thread) */
+/* A GROUP context over the first n_devices CUDA devices of this process (0 = every visible device): the drop-in
+ * for a single-process host that wants all GPUs of the box behind one softray_render -- the reference fans the
+ * rows of one Render() out to rayTraceConcurrency tasks that share surface.Pixels (Renderer.cs:1655-1680).
+ * softray_scene_create builds the scene once and replicates it device-to-device; softray_render cuts
+ * [start_row,end_row] into interleaved row bands, one set per device, and every device stores its bands into the
+ * caller's surface (directly over its own PCIe link when the surface is page-locked: softray_host_register);
+ * statistics are summed (times: the slowest device).  softray_render_device on a group is synchronous and needs a
+ * framebuffer every device can store into: softray_device_alloc on the group (device 0's memory, peer-mapped).
+ * softray_frame.band_count must be <= 1: the group partitions the rows itself. */
+int  softray_create_multi(int32_t n_devices, softray_ctx** out);
+int  softray_device_count(const softray_ctx* ctx);   /* 1 for a softray_create context */
 const char* softray_last_error(const softray_ctx* ctx);
 int  softray_abi_version(void);
 /* sizeof of the PODs below as this library was compiled: 0 mesh, 1 sphere, 2 scene_desc,

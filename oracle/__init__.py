@@ -47,6 +47,8 @@ class Options(C.Structure):
         ("tree_max_per_node", C.c_int32),
         ("path_tracing", C.c_int32),
         ("_pad", C.c_int32),
+        ("col_start", C.c_int32),
+        ("col_end", C.c_int32),
     ]
 
 

@@ -1051,6 +1051,7 @@ void orc_options_defaults(orc_options* o)
     o->tree_max_per_node = 25;
     o->path_tracing = 0;
     o->_pad = 0;
+    o->col_start = 0; o->col_end = -1;
 }
 
 void orc_scene_free(orc_scene* s)
@@ -1423,6 +1424,7 @@ typedef struct {
     const orc_scene* s; const softray_frame* f; const orc_options* o; const inst_ctx* ic; const vec* offsets;
     uint32_t* pixels; int32_t* hit_ids; const orc_aux* aux;
     int start_row, end_row, block_h, n_units;
+    int col_start, col_end, col_chunk, chunks_per_row;   /* non-path-tracing: a unit is a run of col_chunk pixels of one row */
     atomic_int next;
     pthread_mutex_t lock;
     counters_t total;
@@ -1437,6 +1439,15 @@ static void* render_worker(void* arg)
         if (u >= j->n_units) break;
         orc_random rng; orc_random_init(&rng, j->f->random_seed);   /* per block (Renderer.cs:1693) */
         rctx x = { j->s, j->f, j->o, j->ic, j->f->n_instances, j->offsets, &rng, &c };
+        if (j->chunks_per_row > 0) {
+            /* no render-time RNG on this path: any partition of the pixels gives the same image */
+            const int row = j->start_row + u / j->chunks_per_row;
+            const int c0 = j->col_start + (u % j->chunks_per_row) * j->col_chunk;
+            if (j->f->band_count > 1 && j->f->band_height > 0 &&
+                ((row - j->start_row) / j->f->band_height) % j->f->band_count != j->f->band_index) continue;
+            for (int col = c0; col < c0 + j->col_chunk && col <= j->col_end; col++) render_pixel(&x, col, row, j->pixels, j->hit_ids, j->aux);
+            continue;
+        }
         int top = j->start_row + u * j->block_h;
         /* the reference's last block runs blockHeight rows even past end_row (App. A #16); only
          * rows inside [start_row,end_row] are produced here */
@@ -1511,9 +1522,14 @@ int orc_render(const orc_scene* s, const softray_frame* f, const orc_options* op
             job.block_h = (num_rows - 1 + conc) / conc;
             job.n_units = (num_rows - 1 + job.block_h) / job.block_h;
         } else {
-            /* no render-time RNG on this path: any row partition gives the same image */
+            /* no render-time RNG on this path: any partition gives the same image -- runs of 32 pixels */
+            job.col_start = o.col_start < 0 ? 0 : o.col_start;
+            job.col_end = (o.col_end < 0 || o.col_end > f->width - 1) ? f->width - 1 : o.col_end;
+            job.col_chunk = 32;
+            job.chunks_per_row = job.col_end >= job.col_start ? (job.col_end - job.col_start + job.col_chunk) / job.col_chunk : 0;
             job.block_h = 1;
-            job.n_units = num_rows;
+            job.n_units = num_rows * job.chunks_per_row;
+            if (job.chunks_per_row == 0) job.n_units = 0;
         }
         atomic_init(&job.next, 0);
         pthread_mutex_init(&job.lock, NULL);

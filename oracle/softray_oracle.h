@@ -85,6 +85,9 @@ typedef struct orc_options {
     int32_t path_tracing;         /* rayTracePathTracing: oracle-only, used to pin spheres and the
                                      per-block RNG against the reference's pathTracing_* goldens   */
     int32_t _pad;
+    /* test aid: only the columns [col_start, col_end] of each row are produced (col_end < 0: the whole row).  Lets a
+     * test compare a window of a FULL-SIZE frame (the rays of a pixel depend on the frame size) in seconds.       */
+    int32_t col_start, col_end;
 } orc_options;
 void orc_options_defaults(orc_options* o);
 

@@ -48,12 +48,15 @@ using namespace sr;
 // opaque handles
 // ---------------------------------------------------------------------------------------------
 struct softray_ctx {
+    // a GROUP context (softray_create_multi) owns one member context per device and nothing else
+    std::vector<softray_ctx*> members;
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_staged = nullptr;   // the last frame's constants have left the pinned staging
     bool staging_busy = false;
+    bool peer_missing = false;         // group: some member cannot store into member 0's memory (softray_render_device needs it)
     // every frame of a context shares d_insts / d_tile_counter / d_counters: a frame enqueued on another stream
     // than the previous one first waits for that one's kernel (softray_render_device is asynchronous)
     cudaEvent_t ev_frame = nullptr;
@@ -92,6 +95,10 @@ struct softray_ctx {
 };
 
 struct softray_scene {
+    // a scene created in a group context: one replica per member (replicas[i] lives in ctx->members[i])
+    std::vector<softray_scene*> replicas;
+    std::vector<size_t> alloc_bytes;   // size of allocs[i]
+    std::vector<DevMesh> host_meshes;  // host copy of dev.meshes (replication patches its pointers)
     softray_ctx* ctx = nullptr;
     DevScene dev;                      // passed to the kernel by value
     std::vector<void*> allocs;         // every device allocation of this scene
@@ -301,7 +308,7 @@ int upload(softray_scene* sc, const std::vector<T>& host, const T** out)
     void* d = nullptr;
     const size_t bytes = host.size() * sizeof(T);
     SR_CUDA(sc->ctx, cudaMalloc(&d, bytes));
-    sc->allocs.push_back(d);
+    sc->allocs.push_back(d); sc->alloc_bytes.push_back(bytes);
     sc->device_bytes += bytes;
     SR_CUDA(sc->ctx, cudaMemcpyAsync(d, host.data(), bytes, cudaMemcpyHostToDevice, sc->ctx->stream));
     SR_CUDA(sc->ctx, cudaStreamSynchronize(sc->ctx->stream));
@@ -451,6 +458,11 @@ extern "C" void softray_destroy(softray_ctx* ctx)
         for (softray_scene* sc : orphans) g_live_scenes.erase(sc);
     }
     for (softray_scene* sc : orphans) release_scene(sc);
+    if (!ctx->members.empty()) {                        // a group: its members hold every CUDA resource
+        for (softray_ctx* m : ctx->members) softray_destroy(m);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_insts); cudaFree(ctx->d_offsets); cudaFree(ctx->d_tile_counter); cudaFree(ctx->d_counters);
@@ -532,6 +544,11 @@ extern "C" void softray_scene_destroy(softray_scene* scene)
 
 static void release_scene(softray_scene* scene)
 {
+    if (!scene->replicas.empty()) {                     // a group's scene owns its per-device replicas
+        for (softray_scene* r : scene->replicas) softray_scene_destroy(r);
+        delete scene;
+        return;
+    }
     if (scene->ctx) {
         cudaSetDevice(scene->ctx->device);
         cudaStreamSynchronize(scene->ctx->stream);
@@ -577,9 +594,10 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
             if (status == 1) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: vertex index out of range");
             if (status == 2) return fail(ctx, SOFTRAY_E_VERTEX_OUTSIDE_BBOX, "A triangle vertex is outside the bounding box");
             if (status == 3) return fail(ctx, SOFTRAY_E_UNSUPPORTED, "softray_scene_create: device-built tree too deep (use SOFTRAY_ACCEL_BVH)");
-            sc->allocs.push_back(d_tris); sc->allocs.push_back(d_filt); sc->allocs.push_back(d_nodes);
             const size_t b_tris = sizeof(TriRec) * (size_t)m.n_tris, b_filt = sizeof(TriFilt) * (size_t)m.n_tris,
                          b_nodes = sizeof(BvhNode) * (size_t)n_nodes;
+            sc->allocs.push_back(d_tris); sc->allocs.push_back(d_filt); sc->allocs.push_back(d_nodes);
+            sc->alloc_bytes.push_back(b_tris); sc->alloc_bytes.push_back(b_filt); sc->alloc_bytes.push_back(b_nodes);
             sc->device_bytes += b_tris + b_filt + b_nodes;
             sc->unhashed.push_back({d_tris, b_tris}); sc->unhashed.push_back({d_nodes, b_nodes}); sc->unhashed.push_back({d_filt, b_filt});
             dm.tris = d_tris; dm.filt = d_filt; dm.nodes = d_nodes; dm.n_nodes = n_nodes;
@@ -713,6 +731,7 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
             fnv(&sc->fingerprint, dm.bmax, sizeof dm.bmax);
         }
         const uint64_t keep = sc->fingerprint;
+        sc->host_meshes = meshes;
         int rc = upload(sc, meshes, &ds.meshes);
         sc->fingerprint = keep;
         if (rc != SOFTRAY_OK) return rc;
@@ -720,10 +739,13 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
     return SOFTRAY_OK;
 }
 
+static int group_scene_create(softray_ctx* group, const softray_scene_desc* desc, softray_scene** out);
+
 extern "C" int softray_scene_create(softray_ctx* ctx, const softray_scene_desc* desc, softray_scene** out)
 {
     if (!ctx || !desc || !out) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: NULL argument");
     *out = nullptr;
+    if (!ctx->members.empty()) return group_scene_create(ctx, desc, out);
     if (desc->n_meshes < 0 || desc->n_spheres < 0 || (desc->n_meshes > 0 && !desc->meshes) ||
         (desc->n_spheres > 0 && !desc->spheres))
         return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_scene_create: bad counts or NULL arrays");
@@ -751,6 +773,7 @@ extern "C" int softray_scene_create(softray_ctx* ctx, const softray_scene_desc* 
 extern "C" int softray_scene_fingerprint(const softray_scene* scene, uint64_t* out)
 {
     if (!scene || !out) return fail(nullptr, SOFTRAY_E_INVALID_ARG, "softray_scene_fingerprint: NULL argument");
+    if (!scene->replicas.empty()) return softray_scene_fingerprint(scene->replicas[0], out);     // (replicas are byte copies)
     softray_scene* sc = const_cast<softray_scene*>(scene);
     if (!sc->unhashed.empty()) {           // device-built buffers: read them back once
         SR_CUDA(sc->ctx, cudaSetDevice(sc->ctx->device));
@@ -763,6 +786,128 @@ extern "C" int softray_scene_fingerprint(const softray_scene* scene, uint64_t* o
         sc->unhashed.clear();
     }
     *out = scene->fingerprint;
+    return SOFTRAY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU inside ONE process: a group context (`softray_create(n_gpus)`; reference: the row-block
+// fan-out inside one Render(), Renderer.cs:1655-1680).  One member context per device; scenes are built once and
+// replicated device-to-device; a frame is cut into interleaved row bands and every device stores its bands into
+// the caller's surface.  A single host thread drives all devices: every launch and copy is asynchronous.
+// ---------------------------------------------------------------------------------------------
+extern "C" int softray_create_multi(int32_t n_devices, softray_ctx** out)
+{
+    if (!out) return fail(nullptr, SOFTRAY_E_INVALID_ARG, "softray_create_multi: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, SOFTRAY_E_NO_DEVICE, "softray_create_multi: no CUDA device (there is no CPU fallback)");
+    if (n_devices < 0 || n_devices > n_dev) return fail(nullptr, SOFTRAY_E_INVALID_ARG, "softray_create_multi: more devices asked for than visible");
+    const int n = n_devices == 0 ? n_dev : n_devices;
+    softray_ctx* group = new (std::nothrow) softray_ctx();
+    if (!group) return fail(nullptr, SOFTRAY_E_OOM, "softray_create_multi: out of host memory");
+    { std::lock_guard<std::mutex> lock(g_live_mutex); g_live_ctx.insert(group); }
+    for (int i = 0; i < n; i++) {
+        softray_ctx* m = nullptr;
+        const int rc = softray_create(i, &m);
+        if (rc != SOFTRAY_OK) { softray_destroy(group); return rc; }
+        group->members.push_back(m);
+    }
+    group->device = group->members[0]->device;
+    group->sm_count = group->members[0]->sm_count;
+    // every member may store into member 0's memory (softray_device_alloc on a group: the NVLink gather of
+    // softray_render_device is the kernels' own stores, as with the IPC-mapped framebuffer across processes)
+    for (int i = 1; i < n; i++) {
+        int can = 0;
+        cudaSetDevice(i);
+        if (cudaDeviceCanAccessPeer(&can, i, 0) == cudaSuccess && can) {
+            e = cudaDeviceEnablePeerAccess(0, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+        }
+        cudaGetLastError();
+        if (!can) group->peer_missing = true;
+    }
+    *out = group;
+    return SOFTRAY_OK;
+}
+
+extern "C" int softray_device_count(const softray_ctx* ctx)
+{
+    if (!ctx) return 0;
+    return ctx->members.empty() ? 1 : (int)ctx->members.size();
+}
+
+// a byte copy of `src` on another device, pointers patched
+static int clone_scene(const softray_scene* src, softray_ctx* dst, softray_scene** out)
+{
+    *out = nullptr;
+    SR_CUDA(dst, cudaSetDevice(dst->device));
+    softray_scene* c = new (std::nothrow) softray_scene();
+    if (!c) return fail(dst, SOFTRAY_E_OOM, "softray_scene_create: out of host memory");
+    c->ctx = dst;
+    c->mesh_tris = src->mesh_tris; c->mesh_bmin = src->mesh_bmin; c->mesh_bmax = src->mesh_bmax;
+    c->fingerprint = src->fingerprint; c->device_bytes = src->device_bytes;
+    std::memcpy(c->all_min, src->all_min, sizeof c->all_min); std::memcpy(c->all_max, src->all_max, sizeof c->all_max);
+    auto remap = [&](const void* p) -> void* {
+        if (!p) return nullptr;
+        for (size_t k = 0; k < src->allocs.size(); k++) if (src->allocs[k] == p) return c->allocs[k];
+        return nullptr;
+    };
+    int rc = [&]() -> int {
+        for (size_t k = 0; k < src->allocs.size(); k++) {
+            void* d = nullptr;
+            SR_CUDA(dst, cudaMalloc(&d, src->alloc_bytes[k]));
+            c->allocs.push_back(d); c->alloc_bytes.push_back(src->alloc_bytes[k]);
+            SR_CUDA(dst, cudaMemcpyPeerAsync(d, dst->device, src->allocs[k], src->ctx->device, src->alloc_bytes[k], dst->stream));
+        }
+        c->dev = src->dev;
+        c->dev.spheres = static_cast<const SphereRec*>(remap(src->dev.spheres));
+        c->dev.sphere_nodes = static_cast<const BvhNode*>(remap(src->dev.sphere_nodes));
+        c->dev.sph_filt = static_cast<const float4*>(remap(src->dev.sph_filt));
+        c->dev.meshes = static_cast<const DevMesh*>(remap(src->dev.meshes));
+        c->host_meshes = src->host_meshes;
+        for (DevMesh& m : c->host_meshes) {
+            m.tris = static_cast<const TriRec*>(remap(m.tris)); m.filt = static_cast<const TriFilt*>(remap(m.filt));
+            m.nodes = static_cast<const BvhNode*>(remap(m.nodes));
+        }
+        if (!c->host_meshes.empty())
+            SR_CUDA(dst, cudaMemcpyAsync(const_cast<DevMesh*>(c->dev.meshes), c->host_meshes.data(), sizeof(DevMesh) * c->host_meshes.size(),
+                                         cudaMemcpyHostToDevice, dst->stream));
+        SR_CUDA(dst, cudaStreamSynchronize(dst->stream));
+        return SOFTRAY_OK;
+    }();
+    if (rc != SOFTRAY_OK) { release_scene(c); return rc; }
+    { std::lock_guard<std::mutex> lock(g_live_mutex); g_live_scenes.insert(c); dst->scenes.push_back(c); }
+    *out = c;
+    return SOFTRAY_OK;
+}
+
+static int group_scene_create(softray_ctx* group, const softray_scene_desc* desc, softray_scene** out)
+{
+    softray_scene* first = nullptr;
+    int rc = softray_scene_create(group->members[0], desc, &first);      // flatten + build + upload once
+    if (rc != SOFTRAY_OK) { group->err = group->members[0]->err; return rc; }
+    uint64_t fp = 0;
+    softray_scene_fingerprint(first, &fp);                               // (folds device-built buffers in before they are copied)
+    softray_scene* g = new (std::nothrow) softray_scene();
+    if (!g) { softray_scene_destroy(first); return fail(group, SOFTRAY_E_OOM, "softray_scene_create: out of host memory"); }
+    g->ctx = group;
+    g->replicas.push_back(first);
+    g->dev = first->dev; g->fingerprint = first->fingerprint; g->device_bytes = first->device_bytes; g->mesh_tris = first->mesh_tris;
+    for (size_t i = 1; i < group->members.size(); i++) {
+        softray_scene* r = nullptr;
+        rc = clone_scene(first, group->members[i], &r);
+        if (rc != SOFTRAY_OK) {
+            group->err = group->members[i]->err;
+            for (softray_scene* x : g->replicas) softray_scene_destroy(x);
+            delete g;
+            return rc;
+        }
+        g->replicas.push_back(r);
+    }
+    { std::lock_guard<std::mutex> lock(g_live_mutex); g_live_scenes.insert(g); group->scenes.push_back(g); }
+    *out = g;
     return SOFTRAY_OK;
 }
 
@@ -1092,45 +1237,36 @@ int collect_stats(softray_ctx* ctx, cudaStream_t stream, softray_stats* st, bool
 
 }  // namespace
 
-extern "C" int softray_render_device(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
-                                     uint32_t* d_pixels_argb, int32_t* d_hit_ids, void* stream, softray_stats* stats)
+namespace {
+
+// One frame on one device, split so that a group context can start every member before it waits for any:
+// render_*_begin enqueues everything (asynchronous), render_end waits and reads the counters back.
+struct InFlight { bool launched = false; bool host_path = false; cudaStream_t s = nullptr; };
+
+int render_device_begin(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame, uint32_t* d_pixels_argb,
+                        int32_t* d_hit_ids, cudaStream_t stream, bool timed, InFlight* fl)
 {
-    if (!ctx || !scene || !frame || !d_pixels_argb) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render_device: NULL argument");
-    if (scene->ctx != ctx) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render_device: scene belongs to another context");
-    const auto t0 = std::chrono::steady_clock::now();
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    fl->s = stream ? stream : ctx->stream;
     Prepared p;
     int rc = prepare_frame(ctx, scene, frame, &p);
     if (rc != SOFTRAY_OK) return rc;
-    if (p.empty || p.f.tiles_y == 0) {          // no row of the frame is ours: nothing to launch, all counters zero
-        if (stats) std::memset(stats, 0, sizeof *stats);
-        return SOFTRAY_OK;
-    }
-    rc = enqueue_frame(ctx, scene, p, d_pixels_argb, d_hit_ids, s, stats != nullptr);
+    if (p.empty || p.f.tiles_y == 0) return SOFTRAY_OK;          // no row of the frame is ours: nothing to launch
+    rc = enqueue_frame(ctx, scene, p, d_pixels_argb, d_hit_ids, fl->s, timed);
     if (rc != SOFTRAY_OK) return rc;
-    if (stats) {
-        rc = collect_stats(ctx, s, stats, false);
-        if (rc != SOFTRAY_OK) return rc;
-        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    }
+    fl->launched = true;
     return SOFTRAY_OK;
 }
 
-extern "C" int softray_render(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
-                              uint32_t* pixels_argb, int32_t* hit_ids, softray_stats* stats)
+int render_host_begin(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame, uint32_t* pixels_argb, int32_t* hit_ids,
+                      InFlight* fl)
 {
-    if (!ctx || !scene || !frame || !pixels_argb) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: NULL argument");
-    if (scene->ctx != ctx) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: scene belongs to another context");
-    const auto t0 = std::chrono::steady_clock::now();
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    fl->s = ctx->stream; fl->host_path = true;
     Prepared p;
     int rc = prepare_frame(ctx, scene, frame, &p);
     if (rc != SOFTRAY_OK) return rc;
-    if (p.empty || p.f.tiles_y == 0) {
-        if (stats) std::memset(stats, 0, sizeof *stats);
-        return SOFTRAY_OK;
-    }
+    if (p.empty || p.f.tiles_y == 0) return SOFTRAY_OK;
     const size_t n_px = (size_t)frame->width * (size_t)frame->height;
     // A page-locked (CUDA-registered / cudaHostAlloc'd) caller buffer is mapped into the device's address
     // space: the kernel then stores finished pixels straight into it over PCIe, overlapped with tracing,
@@ -1170,14 +1306,110 @@ extern "C" int softray_render(softray_ctx* ctx, const softray_scene* scene, cons
         }
     }
     SR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
-    if (stats) {
-        rc = collect_stats(ctx, s, stats, true);
-        if (rc != SOFTRAY_OK) return rc;
-        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    } else {
-        SR_CUDA(ctx, cudaStreamSynchronize(s));
-    }
+    fl->launched = true;
     return SOFTRAY_OK;
+}
+
+// wait == false (softray_render_device without stats): leave the frame in flight
+int render_end(softray_ctx* ctx, const InFlight& fl, softray_stats* stats, bool wait)
+{
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    if (!fl.launched) return SOFTRAY_OK;
+    SR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (stats) return collect_stats(ctx, fl.s, stats, fl.host_path);
+    if (wait) SR_CUDA(ctx, cudaStreamSynchronize(fl.s));
+    return SOFTRAY_OK;
+}
+
+// ---- a frame on a group context: interleaved row bands, one set per member device ---------------------------
+// The reference fans the rows of one Render() out to rayTraceConcurrency tasks that all store into the one
+// surface.Pixels (Renderer.cs:1655-1680); here the tasks are the GPUs of the box.
+int group_band_height(const softray_frame* fr, int n)
+{
+    int s = fr->start_row < 0 ? 0 : fr->start_row; if (s > fr->height - 1) s = fr->height - 1;
+    int e = fr->end_row < 0 ? 0 : fr->end_row;     if (e > fr->height - 1) e = fr->height - 1;
+    const int rows = e - s + 1;
+    int bh = rows / (n * 16);                         // ~16 bands per device: background rows spread evenly
+    bh = bh / 4 * 4;                                  // whole 4-row tiles
+    return bh < 4 ? 4 : bh;
+}
+
+void add_stats(softray_stats* total, const softray_stats& st)
+{
+    total->rays_primary += st.rays_primary; total->rays_shadow += st.rays_shadow; total->rays_secondary += st.rays_secondary;
+    total->node_visits += st.node_visits; total->prim_tests += st.prim_tests; total->sphere_tests += st.sphere_tests;
+    total->hits_primary += st.hits_primary; total->shaded_hits += st.shaded_hits; total->launches += st.launches;
+    total->filter_tests += st.filter_tests; total->filter_unsure += st.filter_unsure; total->filter_mismatch += st.filter_mismatch;
+    total->rays_bundled += st.rays_bundled; total->rays_fallback += st.rays_fallback; total->rays_short_listed += st.rays_short_listed;
+    total->ms_kernel = std::fmax(total->ms_kernel, st.ms_kernel); total->ms_h2d = std::fmax(total->ms_h2d, st.ms_h2d);
+    total->ms_d2h = std::fmax(total->ms_d2h, st.ms_d2h);
+    for (int k = 0; k < SOFTRAY_N_STAGES; k++) total->ms_stage[k] = std::fmax(total->ms_stage[k], st.ms_stage[k]);
+}
+
+int group_render(softray_ctx* group, const softray_scene* scene, const softray_frame* frame, uint32_t* pixels, int32_t* ids, bool host,
+                 cudaStream_t stream0, softray_stats* stats)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    const int n = (int)group->members.size();
+    if ((int)scene->replicas.size() != n) return fail(group, SOFTRAY_E_INVALID_ARG, "softray_render: scene was not created in this group context");
+    if (frame->band_count > 1) return fail(group, SOFTRAY_E_INVALID_ARG, "softray_render: a group context partitions the rows itself (band_count must be <= 1)");
+    if (frame->width <= 0 || frame->height <= 0) return fail(group, SOFTRAY_E_INVALID_ARG, "softray_render: bad surface size");
+    const int bh = group_band_height(frame, n);
+    std::vector<InFlight> fl((size_t)n);
+    int rc = SOFTRAY_OK;
+    for (int i = 0; i < n && rc == SOFTRAY_OK; i++) {
+        softray_frame fi = *frame;
+        if (n > 1) { fi.band_height = bh; fi.band_count = n; fi.band_index = i; }
+        softray_ctx* m = group->members[(size_t)i];
+        rc = host ? render_host_begin(m, scene->replicas[(size_t)i], &fi, pixels, ids, &fl[(size_t)i])
+                  : render_device_begin(m, scene->replicas[(size_t)i], &fi, pixels, ids, i == 0 ? stream0 : nullptr, stats != nullptr, &fl[(size_t)i]);
+        if (rc != SOFTRAY_OK) group->err = m->err;
+    }
+    // (wait for whatever was started, also after an error: the caller's buffers must be quiet when we return)
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    for (int i = 0; i < n; i++) {
+        softray_stats st;
+        const int rc2 = render_end(group->members[(size_t)i], fl[(size_t)i], stats ? &st : nullptr, true);
+        if (rc2 != SOFTRAY_OK && rc == SOFTRAY_OK) { rc = rc2; group->err = group->members[(size_t)i]->err; }
+        if (stats && rc2 == SOFTRAY_OK) add_stats(stats, st);
+    }
+    if (stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int softray_render_device(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
+                                     uint32_t* d_pixels_argb, int32_t* d_hit_ids, void* stream, softray_stats* stats)
+{
+    if (!ctx || !scene || !frame || !d_pixels_argb) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render_device: NULL argument");
+    if (scene->ctx != ctx) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render_device: scene belongs to another context");
+    if (!frame->instances) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: frame.instances is NULL");
+    if (!ctx->members.empty())          // (synchronous on a group: every member has finished its bands on return)
+        return group_render(ctx, scene, frame, d_pixels_argb, d_hit_ids, false, static_cast<cudaStream_t>(stream), stats);
+    const auto t0 = std::chrono::steady_clock::now();
+    InFlight fl;
+    int rc = render_device_begin(ctx, scene, frame, d_pixels_argb, d_hit_ids, static_cast<cudaStream_t>(stream), stats != nullptr, &fl);
+    if (rc != SOFTRAY_OK) return rc;
+    rc = render_end(ctx, fl, stats, false);
+    if (rc == SOFTRAY_OK && stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+extern "C" int softray_render(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
+                              uint32_t* pixels_argb, int32_t* hit_ids, softray_stats* stats)
+{
+    if (!ctx || !scene || !frame || !pixels_argb) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: NULL argument");
+    if (scene->ctx != ctx) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: scene belongs to another context");
+    if (!frame->instances) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_render: frame.instances is NULL");
+    if (!ctx->members.empty()) return group_render(ctx, scene, frame, pixels_argb, hit_ids, true, nullptr, stats);
+    const auto t0 = std::chrono::steady_clock::now();
+    InFlight fl;
+    int rc = render_host_begin(ctx, scene, frame, pixels_argb, hit_ids, &fl);
+    if (rc != SOFTRAY_OK) return rc;
+    rc = render_end(ctx, fl, stats, true);
+    if (rc == SOFTRAY_OK && stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1187,6 +1419,7 @@ static_assert(sizeof(cudaIpcMemHandle_t) == SOFTRAY_IPC_HANDLE_BYTES, "IPC handl
 
 extern "C" int softray_device_alloc(softray_ctx* ctx, uint64_t bytes, void** d_ptr_out)
 {
+    if (ctx && !ctx->members.empty()) return softray_device_alloc(ctx->members[0], bytes, d_ptr_out);
     if (!ctx || !d_ptr_out || bytes == 0) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_device_alloc: bad argument");
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     SR_CUDA(ctx, cudaMalloc(d_ptr_out, (size_t)bytes));
@@ -1195,6 +1428,7 @@ extern "C" int softray_device_alloc(softray_ctx* ctx, uint64_t bytes, void** d_p
 
 extern "C" int softray_device_free(softray_ctx* ctx, void* d_ptr)
 {
+    if (ctx && !ctx->members.empty()) return softray_device_free(ctx->members[0], d_ptr);
     if (!ctx) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_device_free: NULL context");
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     SR_CUDA(ctx, cudaFree(d_ptr));
@@ -1203,6 +1437,7 @@ extern "C" int softray_device_free(softray_ctx* ctx, void* d_ptr)
 
 extern "C" int softray_ipc_export(softray_ctx* ctx, void* d_ptr, char handle[SOFTRAY_IPC_HANDLE_BYTES])
 {
+    if (ctx && !ctx->members.empty()) return softray_ipc_export(ctx->members[0], d_ptr, handle);
     if (!ctx || !d_ptr || !handle) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_ipc_export: NULL argument");
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h;
@@ -1213,6 +1448,7 @@ extern "C" int softray_ipc_export(softray_ctx* ctx, void* d_ptr, char handle[SOF
 
 extern "C" int softray_ipc_open(softray_ctx* ctx, const char handle[SOFTRAY_IPC_HANDLE_BYTES], void** d_ptr_out)
 {
+    if (ctx && !ctx->members.empty()) return softray_ipc_open(ctx->members[0], handle, d_ptr_out);
     if (!ctx || !handle || !d_ptr_out) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_ipc_open: NULL argument");
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h;
@@ -1223,6 +1459,7 @@ extern "C" int softray_ipc_open(softray_ctx* ctx, const char handle[SOFTRAY_IPC_
 
 extern "C" int softray_host_register(softray_ctx* ctx, void* host_ptr, uint64_t n_bytes)
 {
+    if (ctx && !ctx->members.empty()) return softray_host_register(ctx->members[0], host_ptr, n_bytes);
     if (!ctx || !host_ptr || n_bytes == 0) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_host_register: NULL argument");
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     SR_CUDA(ctx, cudaHostRegister(host_ptr, (size_t)n_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
@@ -1232,6 +1469,10 @@ extern "C" int softray_host_register(softray_ctx* ctx, void* host_ptr, uint64_t 
 extern "C" int softray_host_unregister(softray_ctx* ctx, void* host_ptr)
 {
     if (!ctx || !host_ptr) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_host_unregister: NULL argument");
+    if (!ctx->members.empty()) {
+        for (size_t i = 1; i < ctx->members.size(); i++) { cudaSetDevice(ctx->members[i]->device); cudaStreamSynchronize(ctx->members[i]->stream); }
+        return softray_host_unregister(ctx->members[0], host_ptr);
+    }
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->stream) SR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     SR_CUDA(ctx, cudaHostUnregister(host_ptr));
@@ -1267,6 +1508,7 @@ extern "C" int softray_host_barrier(volatile uint32_t* w, uint32_t n_ranks)
 
 extern "C" int softray_ipc_close(softray_ctx* ctx, void* d_ptr)
 {
+    if (ctx && !ctx->members.empty()) return softray_ipc_close(ctx->members[0], d_ptr);
     if (!ctx || !d_ptr) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_ipc_close: NULL argument");
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     SR_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
@@ -1289,6 +1531,7 @@ static int check_resolve(softray_ctx* ctx, const void* src, const void* dst, int
 extern "C" int softray_resolve_device(softray_ctx* ctx, const uint32_t* d_src, int32_t w, int32_t h, int32_t aa, int32_t style,
                                       uint32_t background, uint32_t* d_dst, void* stream)
 {
+    if (ctx && !ctx->members.empty()) return softray_resolve_device(ctx->members[0], d_src, w, h, aa, style, background, d_dst, stream);
     int rc = check_resolve(ctx, d_src, d_dst, w, h, aa, style);
     if (rc != SOFTRAY_OK) return rc;
     if (aa > 1 && d_src == d_dst) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_resolve: dst may alias src only when aa_res == 1");
@@ -1300,6 +1543,7 @@ extern "C" int softray_resolve_device(softray_ctx* ctx, const uint32_t* d_src, i
 extern "C" int softray_resolve(softray_ctx* ctx, const uint32_t* src, int32_t w, int32_t h, int32_t aa, int32_t style,
                                uint32_t background, uint32_t* dst)
 {
+    if (ctx && !ctx->members.empty()) return softray_resolve(ctx->members[0], src, w, h, aa, style, background, dst);
     int rc = check_resolve(ctx, src, dst, w, h, aa, style);
     if (rc != SOFTRAY_OK) return rc;
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1321,6 +1565,7 @@ extern "C" int softray_resolve(softray_ctx* ctx, const uint32_t* src, int32_t w,
 // ---------------------------------------------------------------------------------------------
 extern "C" int softray_measure_fma_peak(softray_ctx* ctx, int32_t fp64, double* tflops_out)
 {
+    if (ctx && !ctx->members.empty()) return softray_measure_fma_peak(ctx->members[0], fp64, tflops_out);
     if (!ctx || !tflops_out) return fail(ctx, SOFTRAY_E_INVALID_ARG, "softray_measure_fma_peak: NULL argument");
     SR_CUDA(ctx, cudaSetDevice(ctx->device));
     SR_CUDA(ctx, measure_fma_peak(fp64 != 0, ctx->sm_count, ctx->stream, tflops_out));

@@ -25,7 +25,7 @@ NVCC_FLAGS = [
 
 # every symbol include/softray_cuda.h declares
 EXPORTS = [
-    "softray_create", "softray_destroy", "softray_last_error", "softray_abi_version", "softray_abi_sizeof",
+    "softray_create", "softray_create_multi", "softray_device_count", "softray_destroy", "softray_last_error", "softray_abi_version", "softray_abi_sizeof",
     "softray_scene_create", "softray_scene_destroy", "softray_scene_fingerprint",
     "softray_render", "softray_render_device", "softray_instance_init", "softray_frame_defaults",
     "softray_device_alloc", "softray_device_free", "softray_ipc_export", "softray_ipc_open", "softray_ipc_close",
@@ -73,6 +73,8 @@ def load():
     L = C.CDLL(SO_PATH)
     vp = C.c_void_p
     L.softray_create.argtypes = [C.c_int32, C.POINTER(vp)]
+    L.softray_create_multi.argtypes = [C.c_int32, C.POINTER(vp)]
+    L.softray_device_count.argtypes = [vp]
     L.softray_destroy.argtypes = [vp]
     L.softray_destroy.restype = None
     L.softray_last_error.argtypes = [vp]
@@ -141,13 +143,19 @@ def load_3ds(data: bytes) -> MeshData:
 class Context:
     """softray_ctx: one CUDA device, its stream and scratch buffers."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, n_devices=None):
+        """device: one CUDA device (softray_create).  n_devices = k: a group context over the first k devices of this
+        process, 0 = all of them (softray_create_multi): scenes are replicated, frames split into row bands."""
         self._h = C.c_void_p()
-        rc = load().softray_create(int(device), C.byref(self._h))
+        if n_devices is None:
+            rc = load().softray_create(int(device), C.byref(self._h))
+        else:
+            rc = load().softray_create_multi(int(n_devices), C.byref(self._h))
         if rc != abi.OK:
             self._h = C.c_void_p()
             _check(rc, None, "softray_create")
-        self.device = int(device)
+        self.device = int(device) if n_devices is None else 0
+        self.n_devices = load().softray_device_count(self._h)
         self._scenes = weakref.WeakSet()     # scenes hold device memory of this context: they go first
 
     def close(self):

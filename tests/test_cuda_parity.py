@@ -283,6 +283,23 @@ def test_error_contracts(lib, ctx, obj_mesh):
     assert e.value.code == abi.E_INVALID_ARG
 
 
+def test_empty_row_range_renders_nothing(lib, ctx, obj_scene):
+    """start_row > end_row after the clamp (Renderer.cs:1652-1653): the reference's row loop runs zero times.
+    Nothing is written, every counter is zero, nothing divides by the empty band (both pipelines, both entry points)."""
+    import os
+
+    for pl in ("fused", "wave"):
+        os.environ["SOFTRAY_PIPELINE"] = pl
+        try:
+            for kw in (dict(start_row=5, end_row=4), dict(start_row=90, end_row=3, band_height=4, band_count=2, band_index=1)):
+                px = np.full((100, 100), 0xDEADBEEF, dtype=np.uint32)
+                out = obj_scene.render(scenario(resolution=100, shadows=True, **kw), pixels=px, want_ids=True)
+                assert (px == 0xDEADBEEF).all() and (out["ids"] == -1).all()
+                assert out["stats"].rays == 0 and out["stats"].launches == 0
+        finally:
+            os.environ.pop("SOFTRAY_PIPELINE", None)
+
+
 def test_empty_scene_and_empty_mesh(lib, ctx):
     """A Model with no triangles renders the background everywhere."""
     empty = MeshData(np.zeros((0, 3)), np.zeros((0, 3), np.int32), np.zeros(0, np.uint32), [-0.5] * 3, [0.5] * 3)
@@ -312,6 +329,57 @@ def test_config2_full_size_rows_against_oracle(lib, ctx):
         sub = dict(pixels=got["pixels"][sl], ids=got["ids"][sl])
         wsub = dict(pixels=want["pixels"][sl], ids=want["ids"][sl], cos_theta=want["cos_theta"][sl])
         assert_parity(sub, wsub, what=f"rows {top}..{top + 1}")
+
+
+def _window_parity(got, orc, p, windows, what):
+    """Windows (row0, row1, col0, col1) of a FULL-SIZE frame against the oracle: the oracle traces exactly those
+    pixels of the same frame (its own start_row / end_row, Renderer.cs:134-136, plus its test-only column window:
+    the reference tree degenerates to brute force at these sizes, a whole row takes minutes)."""
+    import oracle
+
+    for r0, r1, c0, c1 in windows:
+        p.start_row, p.end_row = r0, r1
+        want = orc.render(p, options=oracle.default_options(col_start=c0, col_end=c1), want_ids=True, want_aux=True)
+        sl = (slice(r0, r1 + 1), slice(c0, c1 + 1))
+        sub = dict(pixels=got["pixels"][sl], ids=got["ids"][sl])
+        wsub = dict(pixels=want["pixels"][sl], ids=want["ids"][sl], cos_theta=want["cos_theta"][sl])
+        assert_parity(sub, wsub, what=f"{what} rows {r0}..{r1} cols {c0}..{c1}")
+        assert int((want["ids"][sl] >= 0).sum()) > 0.3 * wsub["ids"].size, "the window should look at geometry"
+    p.start_row, p.end_row = None, None
+
+
+def test_config3_full_size_windows_against_oracle(lib, ctx):
+    """configs[2] exactly as named -- 1M triangles, 3840x2160, 100 soft-shadow rays per hit, 2 mirror bounces,
+    Texture3D -- rendered once at full size; three windows of it against the oracle."""
+    import oracle
+
+    meshes, _, p = synth.config3()
+    got = lib.Scene(ctx, meshes).render(p, want_ids=True)
+    st = got["stats"]
+    assert st.rays_primary == 3840 * 2160 and st.rays_shadow == 100 * st.shaded_hits and st.rays_secondary > 0
+    assert st.launches > 1, "the 4K configuration should run the stage kernels"
+    orc = oracle.Scene(meshes)
+    _window_parity(got, orc, p, [(700, 701, 1850, 1977), (1400, 1401, 1000, 1127), (1079, 1080, 2600, 2727), (1700, 1701, 2000, 2063)], "config3")
+
+
+def test_config5_full_size_windows_against_oracle(lib, ctx):
+    """configs[4] exactly as named -- 10M triangles, 7680x4320, Phong + 1 shadow ray per hit: windows of the full
+    frame against the oracle, and of the same frame rendered as two interleaved row bands."""
+    import oracle
+
+    meshes, _, p = synth.config5()
+    sc = lib.Scene(ctx, meshes)
+    got = sc.render(p, want_ids=True)
+    st = got["stats"]
+    assert st.rays_primary == 7680 * 4320 and st.rays_shadow == st.hits_primary
+    banded = dict(pixels=np.zeros_like(got["pixels"]), ids=np.full_like(got["ids"], -7))
+    for r in range(2):
+        p.band_height, p.band_count, p.band_index = 36, 2, r
+        sc.render(p, pixels=banded["pixels"], ids=banded["ids"])
+    p.band_height, p.band_count, p.band_index = 0, 1, 0
+    assert (banded["pixels"] == got["pixels"]).all() and (banded["ids"] == got["ids"]).all()
+    orc = oracle.Scene(meshes)
+    _window_parity(got, orc, p, [(2160, 2163, 3800, 4055), (1200, 1201, 4900, 5155), (3300, 3303, 1900, 2027)], "config5")
 
 
 def test_config3_full_size_band_invariance(lib, ctx):
