@@ -308,6 +308,7 @@ __device__ __forceinline__ void spawn_from_hit(const WaveArgs& a, const DevInsta
             if (f.shading) color = shade(f, in, pos, normal, color);
             const uint32_t slot = depth * S + sample;
             a.b.slot_color[slot] = color;
+            if (f.shadows) a.b.slot_escaped[slot] = 0u;          // (the shadow kernels add to it)
             a.b.sample_state[sample] = (uint8_t)(0x80u | (depth + 1u));
             if (f.shadows) {
                 const d3 end = vadd(pos, vscale(normal, 0.001));                  // ShadowMethod.cs:150
@@ -517,6 +518,80 @@ __global__ void __launch_bounds__(kWaveThreads) k_fallback(const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // shadow: ShadowMethod.TraceRaysForSoftShadows (ShadowMethod.cs:144-180) over the compacted shading points
 // ---------------------------------------------------------------------------------------------
+// One ShadowMethod ray (sample i of shading point `end`): the filtered any-hit answer.  With suspects (n_sus > 0) the
+// ray tests those triangles only -- walk_filter_any's leaf test; every other triangle is proven missed by the cone
+// walk -- otherwise it walks.  Returns 0 escaped, 1 occluded, 2 cannot tell (then *fb names what the reference
+// arithmetic has to look at).
+__device__ __forceinline__ int shadow_sample(const DevFrame& f, const DevInstance& in, const DevMesh& m, const double* offsets, d3 end, int i,
+                                             const int* suspects, int n_sus, ShadowFallback* fb, Counters* c)
+{
+    d3 start, dir;
+    shadow_ray(f, in, offsets, end, i, &start, &dir);
+    const d3 anchor = f.point_lighting ? end : vadd(start, dir);   // the ray's far end
+    FRay r;
+    int list[kMaxCand] = {-1, -1, -1, -1}; int n_list = 0;
+    int res = fray_setup(m, f.subdivision, anchor, dir, &r);
+    if (res == 1) {
+        if (n_sus > 0) {
+            bool hit = false;
+            unsigned int nf = 0;
+#pragma unroll
+            for (int j = 0; j < kMaxSuspects; j++) {
+                if (j < n_sus && !hit) {
+                    float tau, etau;
+                    nf++;
+                    const int t = tri_filter<false>(m.filt + suspects[j], r, m.scale, r.tmax_hi, &tau, &etau);
+                    if (t == 1) hit = true;
+                    else if (t == 2) { if (n_list < kMaxCand) list[n_list] = suspects[j]; n_list++; }
+                }
+            }
+            c->filter_tests += nf;
+            res = hit ? 1 : (n_list ? 2 : 0);
+        } else {
+            res = walk_filter_any(m.nodes, m.filt, m.n_tris, r, m.scale, list, &n_list, c);
+        }
+    }
+    if (res == 2) {
+        c->filter_unsure++;
+        const bool listed = n_list >= 1 && n_list <= kMaxCand;
+        fb->sample = (uint32_t)i;
+        fb->list[0] = listed ? list[0] : -2; fb->list[1] = listed && n_list > 1 ? list[1] : -1;
+        fb->list[2] = listed && n_list > 2 ? list[2] : -1; fb->list[3] = listed && n_list > 3 ? list[3] : -1;
+    }
+    return res;
+}
+
+// a ray the filter could not decide: onto the fallback list, or (list full) through the reference arithmetic here
+__device__ __forceinline__ void shadow_unsure(const WaveArgs& a, const DevInstance& in, const DevMesh& m, const double* offsets, d3 end,
+                                              bool unsure, const ShadowFallback& fb, int* escaped, Counters* c)
+{
+    if (!__any_sync(0xffffffffu, unsure)) return;
+    const uint32_t at = warp_append(&a.b.counts->n_shadow_fallback, unsure);
+    if (!unsure) return;
+    if (at < a.cap_shadow_fallback) { a.b.shadow_fallback[at] = fb; return; }
+    d3 start, dir;
+    shadow_ray(a.f, in, offsets, end, (int)fb.sample, &start, &dir);
+    int list[kMaxCand]; int n_list = 0;
+    for (int j = 0; j < kMaxCand; j++) if (fb.list[j] >= 0) list[n_list++] = fb.list[j];
+    XCounters xc; xc.stack = c->stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0;
+    xc.filter_unsure = 0; xc.filter_mismatch = 0;
+    if (!occluded_mesh(m, a.f.subdivision, start, dir, n_list ? list : nullptr, n_list, &xc)) (*escaped)++;
+    c->node_visits += xc.node_visits; c->prim_tests += xc.prim_tests;
+}
+
+__device__ __forceinline__ void load_shadow_item(const WaveArgs& a, uint32_t q, d3* end, uint32_t* slot, uint32_t* inst)
+{
+    const ShadowItem* it = a.b.shadow + q;
+    const double2 v0 = ldg2(it, 0);
+    const double v1 = __ldg(reinterpret_cast<const double*>(it) + 2);
+    const uint2 si = __ldg(reinterpret_cast<const uint2*>(it) + 3);
+    *end = mk(v0.x, v0.y, v1); *slot = si.x; *inst = si.y;
+}
+
+// shadow, first pass: one conservative walk of the cone of each shading point's rays (bundle_suspects).  0 suspects:
+// every ray escapes.  1..8: the rays test those triangles, here.  Too many / out of budget: the point goes onto the
+// walk list, whose rays k_shadow_walk traces in small independent pieces.  (One kernel doing both left the frame
+// waiting for single warps that walked 100 long rays one after the other: 10 ms of tail on config3 at any GPU count.)
 template <int MINB>
 __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_constant__ WaveArgs a)
 {
@@ -524,9 +599,6 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_offsets = reinterpret_cast<double*>(smem_raw);
     for (int i = threadIdx.x; i < 3 * f.shadow_samples; i += blockDim.x) s_offsets[i] = a.offsets[i];
-    __shared__ unsigned int s_bundle_score[2];
-    __shared__ uint32_t s_group;
-    if (threadIdx.x == 0) { s_bundle_score[0] = 0u; s_bundle_score[1] = 0u; }
     __syncthreads();
     const DevInstance* __restrict__ insts = a.insts;
     int walk_stack[kStackEntries];
@@ -535,8 +607,8 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_cons
     const uint32_t n_items = __ldg(&a.b.counts->n_shadow);
     const int n = f.shadow_samples;
     unsigned int n_listed = 0;
-    // a warp takes 32 consecutive shading points (neighbouring pixels: their rays towards sample i of the light run
-    // side by side) and walks the n samples with them; warps fetch their groups from a queue
+    // a warp takes 32 consecutive shading points (neighbouring pixels: their cones run side by side); warps fetch
+    // their groups from a queue
     for (;;) {
         uint32_t group = 0;
         if (lane_id() == 0) group = atomicAdd(&a.b.counts->shadow_head, 1u);
@@ -545,99 +617,94 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_cons
         const uint32_t q = group * 32u + lane_id();
         const bool active = q < n_items;
         d3 end = mk(0, 0, 0); uint32_t slot = 0, inst = 0;
-        if (active) {
-            const ShadowItem* it = a.b.shadow + q;
-            const double2 v0 = ldg2(it, 0);
-            const double v1 = __ldg(reinterpret_cast<const double*>(it) + 2);
-            const uint2 si = __ldg(reinterpret_cast<const uint2*>(it) + 3);
-            end = mk(v0.x, v0.y, v1); slot = si.x; inst = si.y;
-        }
+        if (active) load_shadow_item(a, q, &end, &slot, &inst);
         const DevInstance& in = insts[inst];
         const DevMesh& m = a.sc.meshes[in.mesh];
         int escaped = 0;
-        // one conservative walk of the cone of this point's rays (bundle_suspects): 0 suspects = every ray escapes,
-        // 1..8 = the rays test those triangles only, -1 = the rays walk.  The block keeps the score of the cone
-        // walks (shade_and_shadow in sr_render.cu): where they keep failing, most points stop trying.
         int suspects[kMaxSuspects];
         int n_sus = -1;
-        if (active && f.point_lighting && f.bundle_budget > 0) {
-            const unsigned int ok = s_bundle_score[0], bad = s_bundle_score[1];
-            c.bundle_skip++;
-            if (bad < 64u || ok * 8u >= bad || (c.bundle_skip & 63) == 0) {
-                const d3 light = mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]);
-                n_sus = bundle_suspects(m, end, light, f.light_radius, f.bundle_budget, suspects, &c);
-                if (n_sus == 0) c.bundled += (unsigned int)n;
-                if (n_sus > 0) n_listed += (unsigned int)n;
-                atomicAdd(&s_bundle_score[n_sus >= 0 ? 0 : 1], 1u);
-            }
+        if (active) {
+            const d3 light = mk(in.light_pos_model[0], in.light_pos_model[1], in.light_pos_model[2]);
+            n_sus = bundle_suspects(m, end, light, f.light_radius, f.bundle_budget, suspects, &c);
+            if (n_sus == 0) { c.bundled += (unsigned int)n; escaped = n; }
+            if (n_sus > 0) n_listed += (unsigned int)n;
         }
-        if (n_sus == 0) escaped = n;
-        const bool walk_rays = active && n_sus != 0;
-        for (int i = 0; i < n; i++) {
-            bool unsure = false;
-            ShadowFallback fb;
-            if (walk_rays) {
-                d3 start, dir;
-                shadow_ray(f, in, s_offsets, end, i, &start, &dir);
-                const d3 anchor = f.point_lighting ? end : vadd(start, dir);   // the ray's far end
-                FRay r;
-                int list[kMaxCand] = {-1, -1, -1, -1}; int n_list = 0;
-                int res = fray_setup(m, f.subdivision, anchor, dir, &r);
-                if (res == 1) {
-                    if (n_sus > 0) {
-                        // walk_filter_any's leaf test over the suspects: every other triangle is proven missed
-                        bool hit = false;
-                        unsigned int nf = 0;
-#pragma unroll
-                        for (int j = 0; j < kMaxSuspects; j++) {
-                            if (j < n_sus && !hit) {
-                                float tau, etau;
-                                nf++;
-                                const int t = tri_filter<false>(m.filt + suspects[j], r, m.scale, r.tmax_hi, &tau, &etau);
-                                if (t == 1) hit = true;
-                                else if (t == 2) { if (n_list < kMaxCand) list[n_list] = suspects[j]; n_list++; }
-                            }
-                        }
-                        c.filter_tests += nf;
-                        res = hit ? 1 : (n_list ? 2 : 0);
-                    } else {
-                        res = walk_filter_any(m.nodes, m.filt, m.n_tris, r, m.scale, list, &n_list, &c);
-                    }
+        if (__any_sync(0xffffffffu, n_sus > 0)) {
+            for (int i = 0; i < n; i++) {
+                bool unsure = false;
+                ShadowFallback fb; fb.item = q;
+                if (n_sus > 0) {
+                    const int res = shadow_sample(f, in, m, s_offsets, end, i, suspects, n_sus, &fb, &c);
+                    unsure = res == 2;
+                    if (res == 0) escaped++;
                 }
-                if (res == 2) {
-                    // the reference arithmetic looks at the triangles the filter could not decide (all of them when
-                    // they are too many to list): shadow_fallback
-                    c.filter_unsure++;
-                    unsure = true;
-                    fb.item = q; fb.sample = (uint32_t)i;
-                    const bool listed = n_list >= 1 && n_list <= kMaxCand;
-                    fb.list[0] = listed ? list[0] : -2; fb.list[1] = listed && n_list > 1 ? list[1] : -1;
-                    fb.list[2] = listed && n_list > 2 ? list[2] : -1; fb.list[3] = listed && n_list > 3 ? list[3] : -1;
-                } else if (res == 0) {
-                    escaped++;
-                }
-            }
-            if (__any_sync(0xffffffffu, unsure)) {
-                const uint32_t at = warp_append(&a.b.counts->n_shadow_fallback, unsure);
-                if (unsure) {
-                    if (at < a.cap_shadow_fallback) a.b.shadow_fallback[at] = fb;
-                    else {
-                        // the list is full (it holds one entry per sample of the chunk): answer this ray here
-                        d3 start, dir;
-                        shadow_ray(f, in, s_offsets, end, i, &start, &dir);
-                        int list[kMaxCand]; int n_list = 0;
-                        for (int j = 0; j < kMaxCand; j++) if (fb.list[j] >= 0) list[n_list++] = fb.list[j];
-                        XCounters xc; xc.stack = walk_stack; xc.node_visits = 0; xc.prim_tests = 0; xc.sphere_tests = 0; xc.filter_tests = 0;
-                        xc.filter_unsure = 0; xc.filter_mismatch = 0;
-                        if (!occluded_mesh(m, f.subdivision, start, dir, n_list ? list : nullptr, n_list, &xc)) escaped++;
-                        c.node_visits += xc.node_visits; c.prim_tests += xc.prim_tests;
-                    }
-                }
+                shadow_unsure(a, in, m, s_offsets, end, unsure, fb, &escaped, &c);
             }
         }
         if (active) a.b.slot_escaped[slot] = (uint32_t)escaped;
+        {
+            const bool walk = active && n_sus < 0;
+            const uint32_t at = warp_append(&a.b.counts->n_walk, walk);
+            if (walk) a.b.walk_list[at] = q;
+        }
     }
     const unsigned long long v[14] = {0, 0, 0, c.node_visits, c.prim_tests, 0, 0, 0, c.filter_tests, c.filter_unsure, 0, c.bundled, 0, n_listed};
+    flush_counters(a.counters, v);
+}
+
+// shadow, second pass: the rays of the shading points on the walk list (all of them when the frame has no bundles:
+// fewer than 16 samples per point), kWalkPiece samples of one point per thread.  Consecutive lanes hold consecutive
+// points (neighbouring pixels) and the same samples, so their walks run side by side; the pieces of one point add
+// their escaped rays with one atomic each.
+constexpr int kWalkPiece = 8;
+
+template <int MINB>
+__global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow_walk(const __grid_constant__ WaveArgs a)
+{
+    const DevFrame& f = a.f;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_offsets = reinterpret_cast<double*>(smem_raw);
+    for (int i = threadIdx.x; i < 3 * f.shadow_samples; i += blockDim.x) s_offsets[i] = a.offsets[i];
+    __syncthreads();
+    const DevInstance* __restrict__ insts = a.insts;
+    int walk_stack[kStackEntries];
+    Counters c; c.node_visits = 0; c.prim_tests = 0; c.sphere_tests = 0; c.shaded = 0; c.filter_tests = 0; c.filter_unsure = 0;
+    c.filter_mismatch = 0; c.bundled = 0; c.bundle_skip = 0; c.stack = walk_stack;
+    const bool all_points = f.bundle_budget <= 0 || !f.point_lighting;
+    const uint32_t n_points = all_points ? __ldg(&a.b.counts->n_shadow) : __ldg(&a.b.counts->n_walk);
+    const int n = f.shadow_samples;
+    const uint32_t pieces = (uint32_t)((n + kWalkPiece - 1) / kWalkPiece);
+    const uint32_t groups_per_piece = (n_points + 31u) / 32u;
+    const unsigned long long n_groups = (unsigned long long)groups_per_piece * pieces;
+    for (;;) {
+        uint32_t group = 0;
+        if (lane_id() == 0) group = atomicAdd(&a.b.counts->walk_head, 1u);
+        group = __shfl_sync(0xffffffffu, group, 0);
+        if (group >= n_groups) break;
+        const uint32_t piece = group / groups_per_piece, pg = group - piece * groups_per_piece;
+        const uint32_t w = pg * 32u + lane_id();
+        const bool active = w < n_points;
+        uint32_t q = 0;
+        if (active) q = all_points ? w : a.b.walk_list[w];
+        d3 end = mk(0, 0, 0); uint32_t slot = 0, inst = 0;
+        if (active) load_shadow_item(a, q, &end, &slot, &inst);
+        const DevInstance& in = insts[inst];
+        const DevMesh& m = a.sc.meshes[in.mesh];
+        int escaped = 0;
+        const int i0 = (int)piece * kWalkPiece, i1 = min(n, i0 + kWalkPiece);
+        for (int i = i0; i < i1; i++) {
+            bool unsure = false;
+            ShadowFallback fb; fb.item = q;
+            if (active) {
+                const int res = shadow_sample(f, in, m, s_offsets, end, i, nullptr, 0, &fb, &c);
+                unsure = res == 2;
+                if (res == 0) escaped++;
+            }
+            shadow_unsure(a, in, m, s_offsets, end, unsure, fb, &escaped, &c);
+        }
+        if (active && escaped) atomicAdd(&a.b.slot_escaped[slot], (uint32_t)escaped);
+    }
+    const unsigned long long v[14] = {0, 0, 0, c.node_visits, c.prim_tests, 0, 0, 0, c.filter_tests, c.filter_unsure, 0, 0, 0, 0};
     flush_counters(a.counters, v);
 }
 
@@ -735,6 +802,7 @@ size_t wave_buffer_bytes(uint32_t cap_samples, int max_depth_slots, WaveLayout* 
     lay->ref1 = take(S * sizeof(RefRay));
     lay->shadow = take(S * (size_t)max_depth_slots * sizeof(ShadowItem));
     lay->fallback = take(S * sizeof(uint32_t));
+    lay->walk_list = take(S * (size_t)max_depth_slots * sizeof(uint32_t));
     lay->shadow_fallback = take(S * sizeof(ShadowFallback));      // (capacity checked by the host against the count: see wave_render)
     return off;
 }
@@ -753,6 +821,7 @@ void wave_bind(void* base, const WaveLayout& lay, WaveBufs* b)
     b->ref[1] = reinterpret_cast<RefRay*>(p + lay.ref1);
     b->shadow = reinterpret_cast<ShadowItem*>(p + lay.shadow);
     b->fallback = reinterpret_cast<uint32_t*>(p + lay.fallback);
+    b->walk_list = reinterpret_cast<uint32_t*>(p + lay.walk_list);
     b->shadow_fallback = reinterpret_cast<ShadowFallback*>(p + lay.shadow_fallback);
 }
 
@@ -785,6 +854,25 @@ void launch_hit(int occ, int grid, cudaStream_t st, const WaveArgs& a)
     default: k_hit<SRC, 4><<<grid, kWaveThreads, 0, st>>>(a); break;
     }
 }
+cudaError_t launch_shadow_walk(int occ, int grid, size_t smem, cudaStream_t st, const WaveArgs& a)
+{
+#define SR_WALK_CASE(N)                                                                                                     \
+    case N:                                                                                                                 \
+        if (smem > 48 * 1024) {                                                                                             \
+            cudaError_t e = cudaFuncSetAttribute(k_shadow_walk<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                                 \
+        }                                                                                                                   \
+        k_shadow_walk<N><<<grid, kWaveThreads, smem, st>>>(a);                                                              \
+        break;
+    switch (occ) {
+        SR_WALK_CASE(3) SR_WALK_CASE(4)
+    default:
+        SR_WALK_CASE(5)
+    }
+#undef SR_WALK_CASE
+    return cudaSuccess;
+}
+
 cudaError_t launch_shadow(int occ, int grid, size_t smem, cudaStream_t st, const WaveArgs& a)
 {
 #define SR_SHADOW_CASE(N)                                                                                                   \
@@ -846,7 +934,7 @@ cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance
     const int bounces = (f.reflection_depth > 0 && f.n_instances == 1) ? f.reflection_depth : 0;
     const size_t smem_shadow = sizeof(double) * 3 * (size_t)(f.shadows ? f.shadow_samples : 0);
     const int occ_search = env_occ("SOFTRAY_WAVE_SEARCH_OCC", 4), occ_hit = env_occ("SOFTRAY_WAVE_HIT_OCC", 3),
-              occ_shadow = env_occ("SOFTRAY_WAVE_SHADOW_OCC", 4);
+              occ_shadow = env_occ("SOFTRAY_WAVE_SHADOW_OCC", 4), occ_walk = env_occ("SOFTRAY_WAVE_WALK_OCC", 4);
     const int persistent = sm_count * 8;          // grid of the list kernels (grid-stride over a device-side count)
     int n_launch = 0;
     StageTimer none;
@@ -888,7 +976,11 @@ cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance
             n_launch += 3;
         }
         if (f.shadows) {
-            if ((e = launch_shadow(occ_shadow, sm_count * occ_shadow, smem_shadow, st, a)) != cudaSuccess) return e;
+            // cone walks first (frames with bundles), then the rays of the points they could not settle
+            if (f.bundle_budget > 0 && f.point_lighting)
+                if ((e = launch_shadow(occ_shadow, sm_count * occ_shadow, smem_shadow, st, a)) != cudaSuccess) return e;
+            if ((e = launch_shadow_walk(occ_walk, sm_count * occ_walk, smem_shadow, st, a)) != cudaSuccess) return e;
+            n_launch += 1;
             tm.mark(6);
             k_shadow_fallback<<<persistent, kWaveThreads, 0, st>>>(a); tm.mark(7);
             n_launch += 2;

@@ -36,8 +36,9 @@ struct WaveCounts {
     uint32_t n_shadow;            // shading points in `shadow`
     uint32_t shadow_head;         // next group of 32 shading points the shadow kernel hands to a warp
     uint32_t n_shadow_fallback;
+    uint32_t n_walk, walk_head;   // shading points whose rays have to walk; next group k_shadow_walk hands out
     uint32_t n_fallback[8];       // per bounce: rays the candidate search could not bracket
-    uint32_t _pad[3];
+    uint32_t _pad[1];
 };
 
 struct WaveBufs {
@@ -51,10 +52,11 @@ struct WaveBufs {
     RefRay* ref[2];
     ShadowItem* shadow;
     uint32_t* fallback;
+    uint32_t* walk_list;          // positions in `shadow` of the points the cone walks could not settle
     ShadowFallback* shadow_fallback;
 };
 
-struct WaveLayout { size_t counts, cand, meta, slot_color, slot_escaped, sample_state, sample_id, ref0, ref1, shadow, fallback, shadow_fallback; };
+struct WaveLayout { size_t counts, cand, meta, slot_color, slot_escaped, sample_state, sample_id, ref0, ref1, shadow, fallback, walk_list, shadow_fallback; };
 
 struct WaveArgs {
     DevFrame f;
