@@ -960,7 +960,9 @@ cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance
         if ((e = cudaMemsetAsync(wb.counts, 0, sizeof(WaveCounts), st)) != cudaSuccess) return e;
         // (grid-stride loops: a thread takes several rays, the per-thread prologue / counter flush is paid once)
         const int grid_need = (int)((a.n_rays + kWaveThreads - 1) / kWaveThreads);
-        const int grid_cam = grid_need < sm_count * 32 ? grid_need : sm_count * 32;
+        // every thread the same number of rays: the walks are long, a thread with one ray more is the kernel's tail
+        const int per_thread = (grid_need + sm_count * 32 - 1) / (sm_count * 32);
+        const int grid_cam = (grid_need + per_thread - 1) / per_thread;
         tm.mark(-1);
         launch_search<0>(occ_search, grid_cam, st, a); tm.mark(0);
         launch_hit<0>(occ_hit, grid_cam, st, a); tm.mark(1);
