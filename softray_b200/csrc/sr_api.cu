@@ -1114,6 +1114,15 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
     f.fd_per_tile = make_fastdiv(32u * (uint32_t)(f.sub_pixel_res * f.sub_pixel_res));
     f.fd_tiles_x = make_fastdiv((uint32_t)f.tiles_x); f.fd_tiles_per_band = make_fastdiv((uint32_t)f.tiles_per_band);
     p->smem = sizeof(DevInstance) * (size_t)f.n_instances + sizeof(double) * 3 * (size_t)f.shadow_samples;
+    {   // Small sphere sets are staged in shared memory by every block of the fused kernel (single-instance frames, filter
+        // on) -- as long as that does not cost a resident block: config2's 1000 spheres (80 KB of tree + records) measured
+        // 0.526 -> 0.692 ms staged (2 instead of 3 blocks per SM, and L1 already serves the walk), so the default limit
+        // is 32 KB (~350 spheres); SOFTRAY_STAGE_SPHERES_MAX overrides it.
+        const size_t stage_bytes = sizeof(BvhNode) * (size_t)scene->dev.n_sphere_nodes + sizeof(float4) * (size_t)scene->dev.n_spheres;
+        f.stage_spheres = (scene->dev.n_spheres > kTinyMesh && scene->dev.sphere_nodes != nullptr && scene->dev.sph_filt != nullptr && fr->n_instances == 1 &&
+                           f.filter_mode != SOFTRAY_FILTER_OFF && stage_bytes <= (size_t)env_int("SOFTRAY_STAGE_SPHERES_MAX", 32 * 1024)) ? 1 : 0;
+        if (f.stage_spheres) p->smem = ((p->smem + 63) & ~(size_t)63) + stage_bytes;
+    }
     int occ = render_kernel_occupancy((int)p->smem);
     if (occ < 1) occ = 1;
     { const int cap = env_int("SOFTRAY_BLOCKS_PER_SM", 0); if (cap > 0 && cap < occ) occ = cap; }   // experiments

@@ -356,7 +356,8 @@ __device__ __forceinline__ float cull_from(double limit, double t_off)
 #ifndef SR_WALK_MODE
 #define SR_WALK_MODE 0     // 0: one node or one leaf per iteration ("if-if"); 1: "while-while" (the stage kernels)
 #endif
-template <class BOX, class LEAF>
+// GLOBAL = false: `nodes` is a block's shared-memory copy of a small tree (plain loads, nothing to prefetch)
+template <bool GLOBAL = true, class BOX, class LEAF>
 __device__ __forceinline__ unsigned int walk_bvh(const BvhNode* __restrict__ nodes, int n_prims, int* __restrict__ stack, BOX box,
                                                  LEAF leaf)
 {
@@ -406,8 +407,8 @@ __device__ __forceinline__ unsigned int walk_bvh(const BvhNode* __restrict__ nod
     for (;;) {
         if (cur >= 0) {
             const float4* p = reinterpret_cast<const float4*>(nodes + cur);
-            const float4 a = __ldg(p), b = __ldg(p + 1), cc = __ldg(p + 2);
-            const int2 d = __ldg(reinterpret_cast<const int2*>(p + 3));
+            const float4 a = GLOBAL ? __ldg(p) : p[0], b = GLOBAL ? __ldg(p + 1) : p[1], cc = GLOBAL ? __ldg(p + 2) : p[2];
+            const int2 d = GLOBAL ? __ldg(reinterpret_cast<const int2*>(p + 3)) : *reinterpret_cast<const int2*>(p + 3);
             nv++;
             float t0, t1;
             const bool h0 = box(a.x, a.y, a.z, a.w, b.x, b.y, &t0);
@@ -418,7 +419,7 @@ __device__ __forceinline__ unsigned int walk_bvh(const BvhNode* __restrict__ nod
                 stack[sp++] = far;
 #if SR_PREFETCH >= 1
                 // the far child is needed after the whole near subtree: start its fetch now
-                if (far >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + far));
+                if (GLOBAL && far >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + far));
 #endif
                 cur = first0 ? d.x : d.y;
                 continue;
@@ -805,10 +806,11 @@ __device__ __forceinline__ void walk_filter_closest(const BvhNode* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 struct SRay { float inv_len, T0; };
 
+template <bool GLOBAL = true>
 __device__ __forceinline__ int sphere_filter(const float4* __restrict__ rec, const FRay& r, const SRay& sr, float V, float* lo,
                                              float* hi)
 {
-    const float4 q = __ldg(rec);
+    const float4 q = GLOBAL ? __ldg(rec) : *rec;
     const float ox = r.ox - q.x, oy = r.oy - q.y, oz = r.oz - q.z;
     const float e_o = (3.0f * kU) * (r.oinf + V);
     const float o1 = fabsf(ox) + fabsf(oy) + fabsf(oz);
@@ -836,9 +838,12 @@ __device__ __forceinline__ int sphere_filter(const float4* __restrict__ rec, con
 // The sphere part of rootGeometry for one ray.  ANY: is there a sphere with rayFrac <= 1.0 (shadow rays)?
 // returns 0 no, 1 yes, 2 cannot tell.  !ANY: nearest sphere -> candidates, as walk_filter_closest.
 // In both cases list[0..*n_list) names the spheres the exact arithmetic has to look at (> kMaxCand: all).
-template <bool ANY>
-__device__ __forceinline__ int spheres_filter(const DevScene& sc, d3 s, d3 dir, int* list, int* n_list, unsigned int* nv_out,
-                                              unsigned int* nf_out, int* stack)
+// a block's shared-memory copy of a small sphere set's tree and filter records (sr_render.cu stages it)
+struct SphereStage { const BvhNode* nodes; const float4* filt; };
+
+template <bool ANY, bool GLOBAL>
+__device__ __forceinline__ int spheres_filter_impl(const DevScene& sc, const BvhNode* __restrict__ nodes, const float4* __restrict__ filt, d3 s,
+                                                   d3 dir, int* list, int* n_list, unsigned int* nv_out, unsigned int* nf_out, int* stack)
 {
     FRay r; double t0;
     *n_list = 0;
@@ -856,8 +861,8 @@ __device__ __forceinline__ int spheres_filter(const DevScene& sc, d3 s, d3 dir, 
     int n = 0, c0 = -1, c1 = -1, c2 = -1, c3 = -1;
     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
     unsigned int nf = 0;
-    *nv_out += walk_bvh(
-        sc.sphere_nodes, sc.n_spheres, stack,
+    *nv_out += walk_bvh<GLOBAL>(
+        nodes, sc.n_spheres, stack,
         [&](float lox, float loy, float loz, float hix, float hiy, float hiz, float* t) {
             return fslab(r, lox, loy, loz, hix, hiy, hiz, t);
         },
@@ -865,7 +870,7 @@ __device__ __forceinline__ int spheres_filter(const DevScene& sc, d3 s, d3 dir, 
             for (int i = 0; i < count; i++) {
                 nf++;
                 float lo, hi;
-                const int res = sphere_filter(sc.sph_filt + first + i, r, sr, sc.sph_scale, &lo, &hi);
+                const int res = sphere_filter<GLOBAL>(filt + first + i, r, sr, sc.sph_scale, &lo, &hi);
                 if (res == 0) continue;
                 if (ANY) {
                     if (res == 1 && hi <= 1.0f) { occluded = true; return true; }
@@ -895,6 +900,14 @@ __device__ __forceinline__ int spheres_filter(const DevScene& sc, d3 s, d3 dir, 
         if (ANY || ls[j] <= best_hi) list[m++] = cs[j];
     *n_list = m;
     return 2;
+}
+
+template <bool ANY>
+__device__ __forceinline__ int spheres_filter(const DevScene& sc, d3 s, d3 dir, int* list, int* n_list, unsigned int* nv_out,
+                                              unsigned int* nf_out, int* stack, const SphereStage* stage = nullptr)
+{
+    if (stage != nullptr) return spheres_filter_impl<ANY, false>(sc, stage->nodes, stage->filt, s, dir, list, n_list, nv_out, nf_out, stack);
+    return spheres_filter_impl<ANY, true>(sc, sc.sphere_nodes, sc.sph_filt, s, dir, list, n_list, nv_out, nf_out, stack);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1192,7 +1205,8 @@ __device__ SR_EX_INLINE void mesh_closest_exact(const DevMesh& m, int subdivisio
 // IRayIntersectable.IntersectRay of rootGeometry for a camera / reflection ray: the nearest hit.
 // limit: mesh hits with a rayFrac beyond it cannot matter to the caller (kNoHit: none).  Only prunes the search.
 __device__ SR_CH_INLINE bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, int filter_mode, d3 s, d3 dir,
-                                            Hit* h, XCounters* c, int sync, double limit = 1.7976931348623157e308)
+                                            Hit* h, XCounters* c, int sync, double limit = 1.7976931348623157e308,
+                                            const SphereStage* stage = nullptr)
 {
     // --- spheres (tested first in list order) ---
     BestPrim bs; bs.rf = kNoHit; bs.k = -1; bs.index = 0x7fffffff;
@@ -1203,7 +1217,7 @@ __device__ SR_CH_INLINE bool closest_hit(const DevScene& sc, const DevMesh& m, i
         int list[kMaxCand]; int n_list = 0;
         if (filter_mode != 1 && sc.sphere_nodes != nullptr) {
             unsigned int nv = 0, nf = 0;
-            known = spheres_filter<false>(sc, s, dir, list, &n_list, &nv, &nf, c->stack);
+            known = spheres_filter<false>(sc, s, dir, list, &n_list, &nv, &nf, c->stack, stage);
             c->node_visits += nv; c->filter_tests += nf;
         }
         SR_SYNC_POINT(sync & 2);

@@ -121,7 +121,8 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
 __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const DevScene& sc, const DevInstance* __restrict__ insts,
                                                      const double* __restrict__ offsets, const d3* starts, const d3* dirs_view_or_world,
                                                      bool dirs_are_view, Counters* c, XCounters* xc, unsigned int* n_shadow,
-                                                     unsigned int* n_secondary, bool* hit_out, int sync, bool valid, unsigned int* bundle_score)
+                                                     unsigned int* n_secondary, bool* hit_out, int sync, bool valid, unsigned int* bundle_score,
+                                                     const SphereStage* stage)
 {
     PixelOut out; out.color = f.background; out.id = -1;
     Hit h; int which = 0; bool hit = false;
@@ -129,7 +130,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
     if (f.n_instances == 1) {
         const DevInstance& in = insts[0];
         dir0 = dirs_are_view ? mul3x3(in.Minv, dirs_view_or_world[0]) : dirs_view_or_world[0];
-        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, xc, sync);
+        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, xc, sync, 1.7976931348623157e308, stage);
     } else {
         // extension: nearest hit across instances, ties to the lowest instance.  Rigid
         // transforms keep |dir|, so every instance's rayFrac is the parameter along dirs_view_or_world[0]
@@ -214,7 +215,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
         const d3 rs = vadd(h.pos, vscale(h.normal, 0.001));
         (*n_secondary)++;
         Hit h2;
-        if (!closest_hit(sc, m, f.subdivision, f.filter_mode, rs, r, &h2, xc, false)) { tail = f.background; have_tail = true; break; }
+        if (!closest_hit(sc, m, f.subdivision, f.filter_mode, rs, r, &h2, xc, false, 1.7976931348623157e308, stage)) { tail = f.background; have_tail = true; break; }
         h = h2; d = r;
         depth++;
     }
@@ -243,6 +244,19 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
         for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
         const int n_off = f.shadows ? 3 * f.shadow_samples : 0;
         for (int i = threadIdx.x; i < n_off; i += blockDim.x) s_offsets[i] = g_offsets[i];
+    }
+    // a small sphere set (config2: 1000 spheres = 16 KB of filter records + their tree) is staged in shared memory:
+    // every camera ray of the block walks it (BASELINE.json north_star: "shared-memory staging of small sphere sets")
+    SphereStage stage_v; const SphereStage* stage = nullptr;
+    if (f.stage_spheres) {
+        const size_t at = (sizeof(DevInstance) * (size_t)f.n_instances + sizeof(double) * 3 * (size_t)(f.shadows ? f.shadow_samples : 0) + 63) & ~(size_t)63;
+        float4* s_nodes = reinterpret_cast<float4*>(smem_raw + at);
+        float4* s_filt = s_nodes + 4 * (size_t)sc.n_sphere_nodes;
+        const float4* gn = reinterpret_cast<const float4*>(sc.sphere_nodes);
+        for (int i = threadIdx.x; i < 4 * sc.n_sphere_nodes; i += blockDim.x) s_nodes[i] = __ldg(gn + i);
+        for (int i = threadIdx.x; i < sc.n_spheres; i += blockDim.x) s_filt[i] = __ldg(sc.sph_filt + i);
+        stage_v.nodes = reinterpret_cast<const BvhNode*>(s_nodes); stage_v.filt = s_filt;
+        stage = &stage_v;
     }
     __syncthreads();
 
@@ -332,7 +346,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
             if (valid) n_primary++;
             bool hit = false;
             const PixelOut s1 = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, valid ? &xc : &xc_void, &n_shadow,
-                                                 &n_secondary, &hit, sync, valid, s_bundle_score);
+                                                 &n_secondary, &hit, sync, valid, s_bundle_score, stage);
             if (!valid) continue;
             if (hit) n_hits++;
             int* pa = s_acc[threadIdx.x >> 5][px];
@@ -380,7 +394,8 @@ cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstan
                           uint32_t* d_pixels, int32_t* d_ids, unsigned int* d_tile_counter, DevCounters* d_counters,
                           int grid_blocks, cudaStream_t stream)
 {
-    const size_t smem = sizeof(DevInstance) * (size_t)f.n_instances + (f.shadows ? sizeof(double) * 3 * (size_t)f.shadow_samples : 0);
+    size_t smem = sizeof(DevInstance) * (size_t)f.n_instances + (f.shadows ? sizeof(double) * 3 * (size_t)f.shadow_samples : 0);
+    if (f.stage_spheres) smem = ((smem + 63) & ~(size_t)63) + sizeof(BvhNode) * (size_t)sc.n_sphere_nodes + sizeof(float4) * (size_t)sc.n_spheres;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -394,6 +409,8 @@ int render_kernel_block_threads() { return SR_THREADS; }
 int render_kernel_occupancy(int smem_bytes)
 {
     int nb = 0;
+    if (smem_bytes > 48 * 1024 &&
+        cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel, SR_THREADS, (size_t)smem_bytes) != cudaSuccess) return 0;
     return nb;
 }

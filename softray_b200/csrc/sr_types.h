@@ -140,6 +140,7 @@ struct DevFrame {
     int32_t filter_mode;        // SOFTRAY_FILTER_*: 0 filter + exact fallback, 1 exact only, 2 verify
     float   light_radius;       // >= the length of every area-light offset (0.2, ShadowMethod.cs:10), rounded up
     int32_t bundle_budget;      // node visits a shadow-bundle cone walk may spend before giving up (0 = no bundles)
+    int32_t stage_spheres;      // 1: the blocks of the fused kernel copy the sphere tree + filter records into shared memory
     int32_t phase_sync;         // 1: the warps of a block meet at barriers between the stages of a camera ray
                                 // (sr_render.cu "Phase synchronisation"); 0: they run free
     // composite frames (n_instances > 1): a BVH over the view-space boxes of the instances, rebuilt per frame

@@ -173,6 +173,28 @@ def test_config2_brute_equals_bvh(lib, ctx):
     assert count_diff(a["pixels"], b["pixels"]) == 0 and (a["ids"] == b["ids"]).all()
 
 
+def test_sphere_set_staged_in_shared_memory(lib, ctx):
+    """A small sphere set is walked from a shared-memory copy of its tree and filter records (north_star: "shared-memory
+    staging of small sphere sets"); the frame is the oracle's, and the one without staging."""
+    import os
+
+    import oracle
+
+    meshes, spheres, p = synth.config2(width=200, height=112, shadow_samples=10, n_spheres=300)
+    sc = lib.Scene(ctx, meshes, spheres)
+    staged = sc.render(p, want_ids=True)
+    os.environ["SOFTRAY_STAGE_SPHERES_MAX"] = "0"
+    try:
+        plain = sc.render(p, want_ids=True)
+    finally:
+        os.environ.pop("SOFTRAY_STAGE_SPHERES_MAX")
+    assert (staged["pixels"] == plain["pixels"]).all() and (staged["ids"] == plain["ids"]).all()
+    assert staged["stats"].node_visits == plain["stats"].node_visits
+    want = oracle.Scene(meshes, spheres).render(p, want_ids=True, want_aux=True)
+    assert_parity(staged, want, what="staged spheres")
+    assert int((want["ids"] <= -2).sum()) > 2000
+
+
 def test_config3_small_against_oracle(lib, ctx):
     """Shadows + 2-bounce mirror reflection + Texture3D (oracle-defined extensions)."""
     import oracle
