@@ -32,7 +32,7 @@ namespace sr {
 cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets,
                           uint32_t* d_pixels, int32_t* d_ids, unsigned int* d_tile_counter, DevCounters* d_counters,
                           int grid_blocks, cudaStream_t stream);
-int render_kernel_occupancy(int smem_bytes);
+int render_kernel_occupancy(int smem_bytes, bool staged);
 int render_kernel_block_threads();
 cudaError_t measure_fma_peak(bool fp64, int sm_count, cudaStream_t stream, double* tflops);
 cudaError_t build_mesh_on_device(const double* h_verts, int32_t n_verts, const int32_t* h_vidx, const uint32_t* h_argb, int32_t n_tris,
@@ -1123,7 +1123,7 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
                            f.filter_mode != SOFTRAY_FILTER_OFF && stage_bytes <= (size_t)env_int("SOFTRAY_STAGE_SPHERES_MAX", 32 * 1024)) ? 1 : 0;
         if (f.stage_spheres) p->smem = ((p->smem + 63) & ~(size_t)63) + stage_bytes;
     }
-    int occ = render_kernel_occupancy((int)p->smem);
+    int occ = render_kernel_occupancy((int)p->smem, f.stage_spheres != 0);
     if (occ < 1) occ = 1;
     { const int cap = env_int("SOFTRAY_BLOCKS_PER_SM", 0); if (cap > 0 && cap < occ) occ = cap; }   // experiments
     const long long n_tiles = (long long)f.tiles_x * f.tiles_y;

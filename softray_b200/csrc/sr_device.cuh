@@ -664,12 +664,20 @@ __device__ __forceinline__ bool fslab(const FRay& r, float lox, float loy, float
 // FWD = false: tau runs against the ray (shadow rays, g = -dir); FWD = true: along it (g = dir), which
 // flips the sign of the plane.  thi: candidates surely beyond it are of no interest (-> 0).
 // On 1 and 2, [*tau_o - *etau_o, *tau_o + *etau_o] contains the exact tau (0 +- 0 when not even that is known).
+#ifndef SR_FILTER_PRELOAD
+#define SR_FILTER_PRELOAD 1     // config5 search 8.01 -> 7.79 ms, config3 shadow 4.83 -> 4.62, config4 unchanged
+#endif
 template <bool FWD>
 __device__ __forceinline__ int tri_filter(const TriFilt* __restrict__ t, const FRay& r, float V, float thi, float* tau_o,
                                           float* etau_o)
 {
     const float4* p = reinterpret_cast<const float4*>(t);
     const float4 q0 = __ldg(p);                                          // n, d
+#if SR_FILTER_PRELOAD
+    // all four 16-byte words of the record at once: the later ones are needed only past the early outs, but a load
+    // issued there is a load waited for (the leaf test runs with few lanes and nothing else to hide the latency)
+    const float4 q3 = __ldg(p + 3), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+#endif
     float gn = __fmaf_rn(r.gz, q0.z, __fmaf_rn(r.gy, q0.y, r.gx * q0.x));
     if (FWD) gn = -gn;
     const float e_gn = (8.0f * kU) * r.g1;
@@ -684,16 +692,22 @@ __device__ __forceinline__ int tri_filter(const TriFilt* __restrict__ t, const F
     const float tau = num * rg;
     const float e_tau = (e_num + fabsf(tau) * e_gn) * rg * 1.1f + (4.0f * kU) * fabsf(tau);
     if (tau - e_tau > thi) return 0;
+#if !SR_FILTER_PRELOAD
     const float4 q3 = __ldg(p + 3);                                      // v1, -
+#endif
     const float wx = __fmaf_rn(r.gx, tau, r.ox) - q3.x, wy = __fmaf_rn(r.gy, tau, r.oy) - q3.y,
                 wz = __fmaf_rn(r.gz, tau, r.oz) - q3.z;
+#if !SR_FILTER_PRELOAD
     const float4 q1 = __ldg(p + 1);                                      // a, a1
+#endif
     if (q1.w < 0.0f) return 0;                                           // zero-area triangle: never hit
     const float k = r.ginf * e_tau + (12.0f * kU) * (r.oinf + r.ginf * fabsf(tau) + V);
     const float sN = __fmaf_rn(wz, q1.z, __fmaf_rn(wy, q1.y, wx * q1.x));
     const float e_s = q1.w * k;
     if (sN < -e_s || sN > 1.0f + e_s) return 0;
+#if !SR_FILTER_PRELOAD
     const float4 q2 = __ldg(p + 2);                                      // b, b1
+#endif
     const float uu = __fmaf_rn(wz, q2.z, __fmaf_rn(wy, q2.y, wx * q2.x));
     const float e_u = q2.w * k;
     if (uu < -e_u) return 0;
@@ -902,11 +916,13 @@ __device__ __forceinline__ int spheres_filter_impl(const DevScene& sc, const Bvh
     return 2;
 }
 
-template <bool ANY>
+// STAGED is a compile-time property of the kernel (sr_render.cu instantiates it both ways): two copies of the walk in
+// one kernel cost the fused kernel 4.5 % on config2 through its instruction cache
+template <bool ANY, bool STAGED = false>
 __device__ __forceinline__ int spheres_filter(const DevScene& sc, d3 s, d3 dir, int* list, int* n_list, unsigned int* nv_out,
                                               unsigned int* nf_out, int* stack, const SphereStage* stage = nullptr)
 {
-    if (stage != nullptr) return spheres_filter_impl<ANY, false>(sc, stage->nodes, stage->filt, s, dir, list, n_list, nv_out, nf_out, stack);
+    if (STAGED) return spheres_filter_impl<ANY, false>(sc, stage->nodes, stage->filt, s, dir, list, n_list, nv_out, nf_out, stack);
     return spheres_filter_impl<ANY, true>(sc, sc.sphere_nodes, sc.sph_filt, s, dir, list, n_list, nv_out, nf_out, stack);
 }
 
@@ -1204,6 +1220,7 @@ __device__ SR_EX_INLINE void mesh_closest_exact(const DevMesh& m, int subdivisio
 
 // IRayIntersectable.IntersectRay of rootGeometry for a camera / reflection ray: the nearest hit.
 // limit: mesh hits with a rayFrac beyond it cannot matter to the caller (kNoHit: none).  Only prunes the search.
+template <bool STAGED = false>
 __device__ SR_CH_INLINE bool closest_hit(const DevScene& sc, const DevMesh& m, int subdivision, int filter_mode, d3 s, d3 dir,
                                             Hit* h, XCounters* c, int sync, double limit = 1.7976931348623157e308,
                                             const SphereStage* stage = nullptr)
@@ -1217,7 +1234,7 @@ __device__ SR_CH_INLINE bool closest_hit(const DevScene& sc, const DevMesh& m, i
         int list[kMaxCand]; int n_list = 0;
         if (filter_mode != 1 && sc.sphere_nodes != nullptr) {
             unsigned int nv = 0, nf = 0;
-            known = spheres_filter<false>(sc, s, dir, list, &n_list, &nv, &nf, c->stack, stage);
+            known = spheres_filter<false, STAGED>(sc, s, dir, list, &n_list, &nv, &nf, c->stack, stage);
             c->node_visits += nv; c->filter_tests += nf;
         }
         SR_SYNC_POINT(sync & 2);

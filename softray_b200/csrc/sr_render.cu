@@ -118,6 +118,7 @@ __device__ __forceinline__ uint32_t shade_and_shadow(const DevFrame& f, const De
 }
 
 // TraceRayComplex (Renderer.cs:1850-1879) for one camera ray (+ mirror bounces, + composite instances)
+template <bool STAGED>
 __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const DevScene& sc, const DevInstance* __restrict__ insts,
                                                      const double* __restrict__ offsets, const d3* starts, const d3* dirs_view_or_world,
                                                      bool dirs_are_view, Counters* c, XCounters* xc, unsigned int* n_shadow,
@@ -130,7 +131,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
     if (f.n_instances == 1) {
         const DevInstance& in = insts[0];
         dir0 = dirs_are_view ? mul3x3(in.Minv, dirs_view_or_world[0]) : dirs_view_or_world[0];
-        hit = closest_hit(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, xc, sync, 1.7976931348623157e308, stage);
+        hit = closest_hit<STAGED>(sc, sc.meshes[in.mesh], f.subdivision, f.filter_mode, starts[0], dir0, &h, xc, sync, 1.7976931348623157e308, stage);
     } else {
         // extension: nearest hit across instances, ties to the lowest instance.  Rigid
         // transforms keep |dir|, so every instance's rayFrac is the parameter along dirs_view_or_world[0]
@@ -215,7 +216,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
         const d3 rs = vadd(h.pos, vscale(h.normal, 0.001));
         (*n_secondary)++;
         Hit h2;
-        if (!closest_hit(sc, m, f.subdivision, f.filter_mode, rs, r, &h2, xc, false, 1.7976931348623157e308, stage)) { tail = f.background; have_tail = true; break; }
+        if (!closest_hit<STAGED>(sc, m, f.subdivision, f.filter_mode, rs, r, &h2, xc, false, 1.7976931348623157e308, stage)) { tail = f.background; have_tail = true; break; }
         h = h2; d = r;
         depth++;
     }
@@ -229,6 +230,7 @@ __device__ __forceinline__ PixelOut trace_camera_ray(const DevFrame& f, const De
 #ifndef SR_MIN_BLOCKS
 #define SR_MIN_BLOCKS (768 / SR_THREADS)     // 768 threads x 85 registers per SM: measured best over the four big configs (profiles/)
 #endif
+template <bool STAGED>
 __global__ void __launch_bounds__(SR_THREADS, SR_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevScene sc, const DevInstance* __restrict__ g_insts, const double* __restrict__ g_offsets,
               uint32_t* __restrict__ pixels, int32_t* __restrict__ hit_ids, unsigned int* __restrict__ tile_counter,
@@ -248,7 +250,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
     // a small sphere set (config2: 1000 spheres = 16 KB of filter records + their tree) is staged in shared memory:
     // every camera ray of the block walks it (BASELINE.json north_star: "shared-memory staging of small sphere sets")
     SphereStage stage_v; const SphereStage* stage = nullptr;
-    if (f.stage_spheres) {
+    if (STAGED) {
         const size_t at = (sizeof(DevInstance) * (size_t)f.n_instances + sizeof(double) * 3 * (size_t)(f.shadows ? f.shadow_samples : 0) + 63) & ~(size_t)63;
         float4* s_nodes = reinterpret_cast<float4*>(smem_raw + at);
         float4* s_filt = s_nodes + 4 * (size_t)sc.n_sphere_nodes;
@@ -345,7 +347,7 @@ render_kernel(const __grid_constant__ DevFrame f, const __grid_constant__ DevSce
             }
             if (valid) n_primary++;
             bool hit = false;
-            const PixelOut s1 = trace_camera_ray(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, valid ? &xc : &xc_void, &n_shadow,
+            const PixelOut s1 = trace_camera_ray<STAGED>(f, sc, s_insts, s_offsets, &start, &dir, is_view, &c, valid ? &xc : &xc_void, &n_shadow,
                                                  &n_secondary, &hit, sync, valid, s_bundle_score, stage);
             if (!valid) continue;
             if (hit) n_hits++;
@@ -397,21 +399,28 @@ cudaError_t launch_render(const DevFrame& f, const DevScene& sc, const DevInstan
     size_t smem = sizeof(DevInstance) * (size_t)f.n_instances + (f.shadows ? sizeof(double) * 3 * (size_t)f.shadow_samples : 0);
     if (f.stage_spheres) smem = ((smem + 63) & ~(size_t)63) + sizeof(BvhNode) * (size_t)sc.n_sphere_nodes + sizeof(float4) * (size_t)sc.n_spheres;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = f.stage_spheres ? cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                        : cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    render_kernel<<<grid_blocks, SR_THREADS, smem, stream>>>(f, sc, d_insts, d_offsets, d_pixels, d_ids, d_tile_counter, d_counters);
+    if (f.stage_spheres) render_kernel<true><<<grid_blocks, SR_THREADS, smem, stream>>>(f, sc, d_insts, d_offsets, d_pixels, d_ids, d_tile_counter, d_counters);
+    else render_kernel<false><<<grid_blocks, SR_THREADS, smem, stream>>>(f, sc, d_insts, d_offsets, d_pixels, d_ids, d_tile_counter, d_counters);
     return cudaGetLastError();
 }
 
 int render_kernel_block_threads() { return SR_THREADS; }
 
-int render_kernel_occupancy(int smem_bytes)
+int render_kernel_occupancy(int smem_bytes, bool staged)
 {
     int nb = 0;
-    if (smem_bytes > 48 * 1024 &&
-        cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel, SR_THREADS, (size_t)smem_bytes) != cudaSuccess) return 0;
+    if (smem_bytes > 48 * 1024) {
+        const cudaError_t e = staged ? cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                                     : cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return 0;
+    }
+    const cudaError_t e = staged ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<true>, SR_THREADS, (size_t)smem_bytes)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, render_kernel<false>, SR_THREADS, (size_t)smem_bytes);
+    if (e != cudaSuccess) return 0;
     return nb;
 }
 
