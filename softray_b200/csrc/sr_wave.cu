@@ -25,6 +25,7 @@
 #define SR_WALK_MODE SR_WAVE_WALK_MODE
 #include "sr_device.cuh"
 #include "sr_wave.h"
+#include "../../include/softray_cuda.h"
 
 #include <cstdlib>
 
@@ -457,6 +458,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_fallback(const __grid_constant
     const DevFrame& f = a.f;
     const DevInstance* __restrict__ insts = a.insts;
     __shared__ int s_list[kWaveThreads / 32][32];
+    __shared__ int s_inst[kWaveThreads / 32][SOFTRAY_MAX_INSTANCES];
     int* list = s_list[threadIdx.x >> 5];
     int walk_stack[kStackEntries];
     unsigned int n_nodes = 0, n_tests = 0, n_shadow = 0, n_secondary = 0, n_hits = 0, n_shaded = 0;
@@ -468,7 +470,44 @@ __global__ void __launch_bounds__(kWaveThreads) k_fallback(const __grid_constant
         batch_ray<SRC>(a, insts, r, &s, &dir, &sample, &depth);
         ExactHit eh; eh.hit = false; eh.inst = 0; eh.k = -1; eh.index = 0x7fffffff; eh.rf = kNoHit; eh.rf_from_clip = 0.0;
         eh.clipped_start = s; eh.dir = dir;
-        for (int i = 0; i < f.n_instances; i++) {
+        // composite frames: only the instances whose view-space box the ray touches (the frame's instance hierarchy,
+        // walked without a cull distance: its boxes are padded like every other box) -- not all of them
+        int n_inst = f.n_instances;
+        bool listed = false;
+        if (f.n_instances > 1 && f.tlas_nodes != nullptr) {
+            FRay tr;
+            tr.ox = tr.oy = tr.oz = 0.0f;
+            tr.gx = __double2float_rn(dir.x); tr.gy = __double2float_rn(dir.y); tr.gz = __double2float_rn(dir.z);
+            tr.ix = __fdiv_rn(1.0f, tr.gx); tr.iy = __fdiv_rn(1.0f, tr.gy); tr.iz = __fdiv_rn(1.0f, tr.gz);
+            tr.nox = tr.noy = tr.noz = 0.0f;
+            tr.tcull = CUDART_INF_F;
+            int* ilist = s_inst[threadIdx.x >> 5];
+            int tstack[kTlasStackEntries];
+            int sp = 0, cur = 0, nl = 0;
+            for (;;) {
+                if (cur >= 0) {
+                    const float4* p = reinterpret_cast<const float4*>(f.tlas_nodes + cur);
+                    const float4 A = __ldg(p), B = __ldg(p + 1), CC = __ldg(p + 2);
+                    const int2 d = __ldg(reinterpret_cast<const int2*>(p + 3));
+                    float t0, t1;
+                    const bool h0 = fslab(tr, A.x, A.y, A.z, A.w, B.x, B.y, &t0);
+                    const bool h1 = fslab(tr, B.z, B.w, CC.x, CC.y, CC.z, CC.w, &t1);
+                    if (h0 && h1) { tstack[sp++] = d.y; cur = d.x; continue; }
+                    if (h0) { cur = d.x; continue; }
+                    if (h1) { cur = d.y; continue; }
+                } else {
+                    const int code = -1 - cur;
+                    const int first = code >> 4, count = code & 15;
+                    for (int j = 0; j < count; j++) { if (nl < SOFTRAY_MAX_INSTANCES) ilist[nl] = __ldg(f.tlas_order + first + j); nl++; }
+                }
+                if (sp == 0) break;
+                cur = tstack[--sp];
+            }
+            __syncwarp();
+            if (nl <= SOFTRAY_MAX_INSTANCES) { n_inst = nl; listed = true; }
+        }
+        for (int ii = 0; ii < n_inst; ii++) {
+            const int i = listed ? s_inst[threadIdx.x >> 5][ii] : ii;
             const DevInstance& in = insts[i];
             const DevMesh& m = a.sc.meshes[in.mesh];
             if (m.n_tris <= 0) continue;
@@ -504,7 +543,7 @@ __global__ void __launch_bounds__(kWaveThreads) k_fallback(const __grid_constant
             if (lane_id() == 0) n_nodes += nv;
             if (best.k < 0) continue;
             const double rf = dadd(best.rf, offset);                                                // SpatialSubdivision.cs:416
-            if (rf < eh.rf) {
+            if (rf < eh.rf || (rf == eh.rf && i < eh.inst)) {                                        // ties: the lowest instance
                 eh.hit = true; eh.inst = i; eh.k = best.k; eh.index = best.index; eh.rf_from_clip = best.rf; eh.rf = rf;
                 eh.clipped_start = ts; eh.dir = di;
             }
