@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow(const __grid_cons
 // fewer than 16 samples per point), kWalkPiece samples of one point per thread.  Consecutive lanes hold consecutive
 // points (neighbouring pixels) and the same samples, so their walks run side by side; the pieces of one point add
 // their escaped rays with one atomic each.
-constexpr int kWalkPiece = 8;
+constexpr int kWalkPiece = 2;        // (8: config3 on 8 GPUs waited 2.6 ms for the longest pieces)
 
 template <int MINB>
 __global__ void __launch_bounds__(kWaveThreads, MINB) k_shadow_walk(const __grid_constant__ WaveArgs a)
