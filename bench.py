@@ -515,7 +515,7 @@ def measure(g, name, steps, warmup, want_e2e=True, sample_clocks=False, check_si
                 ref = _as_tensor(peer.ptr, H, W).cpu().numpy().view(np.uint32)
                 e2e_ok = bool(np.array_equal(ref, shared.pixels))
             shared.close()
-        h2d = 288 * len(frame.instances) + (24 * frame.shadow_samples if frame.shadows else 0)
+        h2d = 320 * len(frame.instances) + (24 * frame.shadow_samples if frame.shadows else 0)
         e2e = {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": W * H * 4,
                "matches_device_frame": e2e_ok,

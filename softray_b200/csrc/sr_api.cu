@@ -406,6 +406,20 @@ inline int env_int(const char* name, int dflt)
 constexpr int kLbvhLeaf = 1;
 inline int lbvh_leaf_max() { const int v = env_int("SOFTRAY_LBVH_LEAF", kLbvhLeaf); return v < 1 ? 1 : (v > kMaxLeafPrims ? kMaxLeafPrims : v); }
 
+// bounding sphere of a mesh around its box centre: radius = the farthest vertex (every triangle is the hull of its vertices)
+inline void mesh_bounding_sphere(const softray_mesh& m, DevMesh* dm)
+{
+    double c[3], r2 = 0.0;
+    for (int k = 0; k < 3; k++) c[k] = 0.5 * (m.bbox_min[k] + m.bbox_max[k]);
+    for (int64_t i = 0; i < (int64_t)m.n_verts; i++) {
+        double d2 = 0.0;
+        for (int k = 0; k < 3; k++) { const double d = m.verts_xyz[3 * i + k] - c[k]; d2 += d * d; }
+        r2 = std::fmax(r2, d2);
+    }
+    for (int k = 0; k < 3; k++) dm->bs_center[k] = c[k];
+    dm->bs_radius = std::sqrt(r2);
+}
+
 inline FastDiv make_fastdiv(uint32_t d)
 {
     FastDiv f; f.d = d ? d : 1u; f._pad = 0; f.mul = 0; f.shift = 0;
@@ -578,6 +592,7 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
                 sc->all_min[k] = std::fmin(sc->all_min[k], m.bbox_min[k]); sc->all_max[k] = std::fmax(sc->all_max[k], m.bbox_max[k]);
             }
             dm.scale = round_up(max_abs3(m.bbox_min, m.bbox_max));
+            mesh_bounding_sphere(m, &dm);
             sc->mesh_tris.push_back(m.n_tris);
             { softray_scene::V3 a, b; for (int k = 0; k < 3; k++) { a.v[k] = m.bbox_min[k]; b.v[k] = m.bbox_max[k]; }
               sc->mesh_bmin.push_back(a); sc->mesh_bmax.push_back(b); }
@@ -635,6 +650,7 @@ static int build_scene(softray_scene* sc, const softray_scene_desc* desc)
             sc->all_min[k] = std::fmin(sc->all_min[k], m.bbox_min[k]); sc->all_max[k] = std::fmax(sc->all_max[k], m.bbox_max[k]);
         }
         dm.scale = round_up(max_abs3(m.bbox_min, m.bbox_max));
+        mesh_bounding_sphere(m, &dm);
         sc->mesh_tris.push_back(m.n_tris);
         { softray_scene::V3 a, b; for (int k = 0; k < 3; k++) { a.v[k] = m.bbox_min[k]; b.v[k] = m.bbox_max[k]; }
           sc->mesh_bmin.push_back(a); sc->mesh_bmax.push_back(b); }
@@ -1069,6 +1085,13 @@ int prepare_frame(softray_ctx* ctx, const softray_scene* scene, const softray_fr
         d.tri_base = base;
         base += scene->mesh_tris[(size_t)in.mesh_id];
         d.sph_can_shadow = (f.shadows && scene->dev.n_spheres > 0) ? spheres_can_shadow(scene, f, d, ctx->h_offsets) : 0;
+        {   // the mesh's bounding sphere in view space (rigid transform: same radius); padded well beyond FP64 rounding
+            const DevMesh& hm = scene->host_meshes[(size_t)in.mesh_id];
+            const hv cv = hmul3x4(in.M, hmk(hm.bs_center[0], hm.bs_center[1], hm.bs_center[2]));
+            d.bs_center_view[0] = cv.x; d.bs_center_view[1] = cv.y; d.bs_center_view[2] = cv.z;
+            const double r = hm.bs_radius * (1.0 + 1e-9) + 1e-9 * (1.0 + std::fabs(cv.x) + std::fabs(cv.y) + std::fabs(cv.z));
+            d.bs_radius2 = r * r;
+        }
     }
 
     // composite frame: BVH over the view-space boxes of the instances (the reference traces

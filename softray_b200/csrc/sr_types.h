@@ -85,6 +85,7 @@ struct DevMesh {
     float   fmin[3], fmax[3];   // the same box rounded to FP32 (nearest)
     float   scale;              // largest |coordinate| of bmin/bmax, rounded up
     int32_t _pad;
+    double  bs_center[3], bs_radius;   // a sphere around the box centre that holds every vertex (tighter than the box for round meshes)
 };
 
 struct DevScene {
@@ -110,6 +111,8 @@ struct DevInstance {
     int32_t tri_base;           // flattened hit-id base
     int32_t sph_can_shadow;     // 0: no sphere can report rayFrac <= 1 for any shadow ray of this frame
     int32_t _pad;
+    double  bs_center_view[3];  // composite frames: the mesh's bounding sphere (DevMesh::bs_*) in view space ...
+    double  bs_radius2;         // ... and its squared radius, padded: a view ray that misses it misses the instance
 };
 
 // n / d for a divisor fixed per frame and n < 2^31: one multiply-high and a shift instead of the ~20-instruction

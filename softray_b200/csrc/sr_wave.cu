@@ -241,6 +241,16 @@ __global__ void __launch_bounds__(kWaveThreads, MINB) k_search(const __grid_cons
                     for (int j = 0; j < count; j++) {
                         const int i = __ldg(f.tlas_order + first + j);
                         const DevInstance& in = insts[i];
+                        {   // the view ray (from the view origin) against the instance's bounding sphere: the hierarchy's boxes are
+                            // the AABBs of rotated boxes, three times the cross-section of a round mesh, and an instance that
+                            // is entered costs a ray set-up and a partial walk (config4: 3.6 of the 4.6 instances a ray enters)
+                            const d3 cv = mk(in.bs_center_view[0], in.bs_center_view[1], in.bs_center_view[2]);
+                            const double b = cv.x * dir.x + cv.y * dir.y + cv.z * dir.z;
+                            const double cc = cv.x * cv.x + cv.y * cv.y + cv.z * cv.z;
+                            const double dd = dir.x * dir.x + dir.y * dir.y + dir.z * dir.z;
+                            const double out2 = cc - in.bs_radius2;                     // > 0: the origin is outside the sphere
+                            if (out2 > 0.0 && (b <= 0.0 || b * b < out2 * dd * (1.0 - 1e-9))) continue;
+                        }
                         search_mesh(a.sc.meshes[in.mesh], f.subdivision, mk(in.start[0], in.start[1], in.start[2]), mul3x3(in.Minv, dir), i,
                                     st, &xc);
                         if (st.best_hi < 1e29f) tr.tcull = st.best_hi * 1.00002f + 1e-6f;
