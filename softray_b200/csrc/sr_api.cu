@@ -91,6 +91,8 @@ struct softray_ctx {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     StageTimer stage_timer;                     // softray_frame.profile_stages
+    cudaStream_t copy_stream = nullptr;         // chunk-by-chunk DMA of a frame into a page-locked host surface
+    std::vector<cudaEvent_t> copy_events;
     std::string err;
 };
 
@@ -310,8 +312,9 @@ int upload(softray_scene* sc, const std::vector<T>& host, const T** out)
     SR_CUDA(sc->ctx, cudaMalloc(&d, bytes));
     sc->allocs.push_back(d); sc->alloc_bytes.push_back(bytes);
     sc->device_bytes += bytes;
+    // (pageable source: the call returns once the bytes are staged, so `host` may die right after; the stream is
+    // synchronised once, at the end of softray_scene_create)
     SR_CUDA(sc->ctx, cudaMemcpyAsync(d, host.data(), bytes, cudaMemcpyHostToDevice, sc->ctx->stream));
-    SR_CUDA(sc->ctx, cudaStreamSynchronize(sc->ctx->stream));
     fnv(&sc->fingerprint, host.data(), bytes);
     *out = static_cast<const T*>(d);
     return SOFTRAY_OK;
@@ -489,6 +492,8 @@ extern "C" void softray_destroy(softray_ctx* ctx)
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -518,6 +523,7 @@ extern "C" int softray_create(int32_t device_ordinal, softray_ctx** out)
         SR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         SR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         SR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        SR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_insts, sizeof(DevInstance) * SOFTRAY_MAX_INSTANCES));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_offsets, sizeof(double) * 3 * SOFTRAY_MAX_SHADOW_SAMPLES));
         SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_tile_counter, sizeof(unsigned int)));
@@ -776,6 +782,10 @@ extern "C" int softray_scene_create(softray_ctx* ctx, const softray_scene_desc* 
         rc = build_scene(sc, desc);
     } catch (const std::bad_alloc&) {
         rc = fail(ctx, SOFTRAY_E_OOM, "softray_scene_create: out of host memory");
+    }
+    if (rc == SOFTRAY_OK) {
+        const cudaError_t e = cudaStreamSynchronize(ctx->stream);        // every upload of the scene has landed
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "softray_scene_create: upload");
     }
     if (rc != SOFTRAY_OK) {
         release_scene(sc);
@@ -1187,7 +1197,7 @@ T* zero_copy_pointer(T* host)
 }
 
 int enqueue_frame(softray_ctx* ctx, const softray_scene* scene, const Prepared& p, uint32_t* d_pixels, int32_t* d_ids,
-                  cudaStream_t stream, bool timed)
+                  cudaStream_t stream, bool timed, uint32_t* h_pixels = nullptr, int32_t* h_ids = nullptr)
 {
     const DevFrame& f = p.f;
     if (ctx->have_last_frame && ctx->last_stream != stream) SR_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_frame, 0));
@@ -1233,10 +1243,15 @@ int enqueue_frame(softray_ctx* ctx, const softray_scene* scene, const Prepared& 
             ctx->wave_bytes = 2 * bytes; ctx->wave_cap = new_cap; ctx->wave_slots = new_slots;
         }
         int launches = 0;
+        HostCopy hc;
+        if (h_pixels) {
+            hc.h_pixels = h_pixels; hc.h_ids = h_ids; hc.d_pixels = d_pixels; hc.d_ids = d_ids;
+            hc.copy_stream = ctx->copy_stream; hc.events = &ctx->copy_events;
+        }
         ctx->stage_timer.on = timed && p.profile;
         SR_CUDA(ctx, wave_render(f, scene->dev, ctx->d_insts, ctx->d_offsets, ctx->wave, (uint32_t)cap, d_pixels, d_ids, ctx->d_counters,
                                  ctx->sm_count, stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join, &launches,
-                                 (timed && p.profile) ? &ctx->stage_timer : nullptr));
+                                 (timed && p.profile) ? &ctx->stage_timer : nullptr, h_pixels ? &hc : nullptr));
         ctx->last_launches = launches;
     } else
     SR_CUDA(ctx, launch_render(f, scene->dev, ctx->d_insts, ctx->d_offsets, d_pixels, d_ids, ctx->d_tile_counter,
@@ -1307,7 +1322,14 @@ int render_host_begin(softray_ctx* ctx, const softray_scene* scene, const softra
     int32_t* zc_ids = hit_ids ? zero_copy_pointer(hit_ids) : nullptr;
     const bool zero_copy = zc_pixels != nullptr && (!hit_ids || zc_ids != nullptr) && !env_int("SOFTRAY_NO_ZERO_COPY", 0);
     cudaStream_t s = ctx->stream;
-    if (zero_copy) {
+    // A big frame of the stage-kernel pipeline leaves chunk by chunk through the copy engines instead: its compose
+    // kernels write HBM at HBM speed and the DMA of chunk i runs under the tracing of chunk i + 1 (kernels storing
+    // 132 MB over PCIe themselves kept their blocks resident for the length of the transfer: config5 e2e 15.2 ms
+    // against 12.1 on the device).
+    const int nn_ = p.f.sub_pixel_res * p.f.sub_pixel_res;
+    const bool chunk_dma = zero_copy && p.wave && !p.profile && n_px >= ((size_t)1 << 21) && p.f.tiles_y >= 4 && !env_int("SOFTRAY_NO_CHUNK_DMA", 0) &&
+                           (long long)p.f.tiles_x * 32 * nn_ <= (long long)env_int("SOFTRAY_WAVE_CHUNK", 1 << 23);
+    if (zero_copy && !chunk_dma) {
         rc = enqueue_frame(ctx, scene, p, zc_pixels, zc_ids, s, true);
         if (rc != SOFTRAY_OK) return rc;
     } else {
@@ -1321,14 +1343,15 @@ int render_host_begin(softray_ctx* ctx, const softray_scene* scene, const softra
             SR_CUDA(ctx, cudaMalloc((void**)&ctx->d_ids, n_px * sizeof(int32_t)));
             ctx->ids_capacity = n_px;
         }
-        rc = enqueue_frame(ctx, scene, p, ctx->d_pixels, hit_ids ? ctx->d_ids : nullptr, s, true);
+        rc = enqueue_frame(ctx, scene, p, ctx->d_pixels, hit_ids ? ctx->d_ids : nullptr, s, true, chunk_dma ? pixels_argb : nullptr,
+                           chunk_dma ? hit_ids : nullptr);
         if (rc != SOFTRAY_OK) return rc;
         // read back exactly the rows that were rendered; banded frames copy each
         // band of this rank separately so the caller's other rows stay untouched
         const size_t W = (size_t)frame->width;
         const bool banded = p.f.band_count > 1;
         const int bh = banded ? p.f.band_height : (p.end_row - p.start_row + 1);
-        for (int top = p.start_row, b = 0; top <= p.end_row; top += bh, b++) {
+        for (int top = p.start_row, b = 0; top <= p.end_row && !chunk_dma; top += bh, b++) {
             if (banded && b % p.f.band_count != p.f.band_index) continue;
             const int last = top + bh - 1 > p.end_row ? p.end_row : top + bh - 1;
             const size_t off = (size_t)top * W, cnt = (size_t)(last - top + 1) * W;

@@ -968,7 +968,7 @@ void StageTimer::collect(double* ms_stage, int n)
 cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets, const WaveBufs bufs[2],
                         uint32_t cap_samples, uint32_t* d_pixels, int32_t* d_ids, DevCounters* d_counters, int sm_count,
                         cudaStream_t stream, cudaStream_t side_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, int* launches,
-                        StageTimer* prof)
+                        StageTimer* prof, const HostCopy* host)
 {
     const int nn = f.sub_pixel_res * f.sub_pixel_res;
     const uint32_t per_tile = 32u * (uint32_t)nn;
@@ -978,8 +978,19 @@ cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance
     const bool profiling = prof != nullptr && prof->on;
     const bool two = side_stream != nullptr && !profiling && env_occ("SOFTRAY_WAVE_STREAMS", 2) >= 2 && n_tiles * per_tile >= (1u << 20);
     if (two && n_chunks < 2) n_chunks = 2;
+    if (host) {     // the last chunk's copy is exposed: more, smaller chunks -- but not below 4 M samples (config3 as 8 chunks: 7.2 -> 8.5 ms)
+        long long want = n_tiles * per_tile / (1ll << 22);
+        if (want > 8) want = 8;
+        if (n_chunks < want) n_chunks = want;
+    }
     if (two && (n_chunks & 1)) n_chunks++;
-    const long long tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
+    long long tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
+    if (host) {     // whole tile rows per chunk: a chunk is then a few runs of pixel rows
+        tiles_per_chunk = (tiles_per_chunk / f.tiles_x) * f.tiles_x;
+        if (tiles_per_chunk < f.tiles_x) tiles_per_chunk = f.tiles_x;
+        if (tiles_per_chunk * per_tile > cap_samples) return cudaErrorInvalidValue;
+    }
+    size_t ev_used = 0;
     const int bounces = (f.reflection_depth > 0 && f.n_instances == 1) ? f.reflection_depth : 0;
     const size_t smem_shadow = sizeof(double) * 3 * (size_t)(f.shadows ? f.shadow_samples : 0);
     const int occ_search = env_occ("SOFTRAY_WAVE_SEARCH_OCC", 4), occ_hit = env_occ("SOFTRAY_WAVE_HIT_OCC", 3),
@@ -1040,6 +1051,51 @@ cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance
         n_launch += 1;
         tm.mark(8);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (host) {
+            // this chunk's rows -> the host surface by DMA, behind an event: the SMs go on with the next chunk
+            if (ev_used >= host->events->size()) {
+                cudaEvent_t ev;
+                if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+                host->events->push_back(ev);
+            }
+            cudaEvent_t ev = (*host->events)[ev_used++];
+            if ((e = cudaEventRecord(ev, st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(host->copy_stream, ev, 0)) != cudaSuccess) return e;
+            const long long ty0 = tile0 / f.tiles_x, ty1 = (tile0 + a.n_tiles) / f.tiles_x;
+            long long run_first = -1, run_last = -1;                 // a run of consecutive pixel rows
+            auto flush = [&]() -> cudaError_t {
+                if (run_first < 0) return cudaSuccess;
+                const size_t off = (size_t)run_first * (size_t)f.width, cnt = (size_t)(run_last - run_first + 1) * (size_t)f.width;
+                cudaError_t ce = cudaMemcpyAsync(host->h_pixels + off, host->d_pixels + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, host->copy_stream);
+                if (ce == cudaSuccess && host->h_ids)
+                    ce = cudaMemcpyAsync(host->h_ids + off, host->d_ids + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, host->copy_stream);
+                run_first = -1;
+                return ce;
+            };
+            for (long long ty = ty0; ty < ty1; ty++) {
+                const long long band_j = ty / f.tiles_per_band;
+                const long long band_top = f.start_row + (f.band_index + band_j * f.band_count) * (long long)f.band_height;
+                const long long r0 = band_top + (ty - band_j * f.tiles_per_band) * 4;
+                long long r1 = r0 + 3;
+                if (r1 > band_top + f.band_height - 1) r1 = band_top + f.band_height - 1;
+                if (r1 > f.end_row) r1 = f.end_row;
+                if (r1 < r0) continue;
+                if (run_first >= 0 && r0 == run_last + 1) { run_last = r1; continue; }
+                if ((e = flush()) != cudaSuccess) return e;
+                run_first = r0; run_last = r1;
+            }
+            if ((e = flush()) != cudaSuccess) return e;
+        }
+    }
+    if (host) {     // the frame's stream ends when the last copy has landed
+        if (ev_used >= host->events->size()) {
+            cudaEvent_t ev;
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+            host->events->push_back(ev);
+        }
+        cudaEvent_t ev = (*host->events)[ev_used++];
+        if ((e = cudaEventRecord(ev, host->copy_stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream, ev, 0)) != cudaSuccess) return e;
     }
     if (two) {
         if ((e = cudaEventRecord(ev_join, side_stream)) != cudaSuccess) return e;

@@ -81,11 +81,20 @@ struct StageTimer {
     void collect(double* ms_stage, int n);      // after the stream has been synchronised
 };
 
+// Host surface of a frame whose chunks leave the GPU by DMA as they finish (softray_render with a page-locked surface):
+// after each chunk's compose kernel its rows are copied device -> host on `copy_stream` while the next chunk traces.
+struct HostCopy {
+    uint32_t* h_pixels = nullptr; int32_t* h_ids = nullptr;          // page-locked host surface (full-frame indexing)
+    const uint32_t* d_pixels = nullptr; const int32_t* d_ids = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t>* events = nullptr;                      // pool, grown on demand (owned by the context)
+};
+
 size_t wave_buffer_bytes(uint32_t cap_samples, int depth_slots, WaveLayout* lay);
 void wave_bind(void* base, const WaveLayout& lay, WaveBufs* b);
 cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance* d_insts, const double* d_offsets, const WaveBufs bufs[2],
                         uint32_t cap_samples, uint32_t* d_pixels, int32_t* d_ids, DevCounters* d_counters, int sm_count,
                         cudaStream_t stream, cudaStream_t side_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, int* launches,
-                        StageTimer* prof);
+                        StageTimer* prof, const HostCopy* host);
 
 }  // namespace sr

@@ -192,3 +192,33 @@ def test_wave_is_the_default_for_big_scenes_and_composites(lib, ctx, obj_scene):
     assert lib.Scene(ctx, meshes).render(p)["stats"].launches > 1
     meshes, _, p = synth.config4(width=64, height=36, n_lon=20, n_lat=10, n_side=2, sub_pixel_res=1)
     assert lib.Scene(ctx, meshes).render(p)["stats"].launches > 1
+
+
+def test_wave_big_frame_leaves_chunk_by_chunk_by_dma(lib, ctx):
+    """A big stage-kernel frame into a page-locked surface is copied out chunk by chunk while the next chunk traces:
+    same pixels and ids as through a pageable surface, only the requested rows / bands touched."""
+    import torch
+
+    meshes, _, p = synth.config3(width=2048, height=1100, nx=301, nz=151, shadow_samples=2)
+    sc = lib.Scene(ctx, meshes)
+    want = sc.render(p, want_ids=True)
+    assert want["stats"].launches > 1
+    px = torch.full((1100, 2048), 0x01020304, dtype=torch.int32).pin_memory()
+    ids = torch.full((1100, 2048), 777, dtype=torch.int32).pin_memory()
+    got = sc.render(p, want_ids=True, pixels=px.numpy().view(np.uint32), ids=ids.numpy())
+    assert np.array_equal(got["pixels"], want["pixels"]) and np.array_equal(got["ids"], want["ids"])
+    for kw in (dict(start_row=101, end_row=1003), dict(band_height=36, band_count=3, band_index=2), dict(start_row=7, end_row=1090, band_height=20, band_count=2, band_index=0)):
+        for k, v in kw.items():
+            setattr(p, k, v)
+        px.fill_(0x01020304)
+        ids.fill_(777)
+        sc.render(p, pixels=px.numpy().view(np.uint32), ids=ids.numpy())
+        s0, e0 = (p.start_row or 0), (p.end_row if p.end_row is not None else 1099)
+        rows = np.arange(1100)
+        mine = (rows >= s0) & (rows <= e0)
+        if p.band_count > 1:
+            mine &= ((rows - s0) // p.band_height) % p.band_count == p.band_index
+        gp, gi = px.numpy().view(np.uint32), ids.numpy()
+        assert np.array_equal(gp[mine], want["pixels"][mine]) and np.array_equal(gi[mine], want["ids"][mine]), kw
+        assert (gp[~mine] == 0x01020304).all() and (gi[~mine] == 777).all(), kw
+        p.start_row, p.end_row, p.band_height, p.band_count, p.band_index = None, None, 0, 1, 0
