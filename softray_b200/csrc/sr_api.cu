@@ -1384,7 +1384,7 @@ int group_band_height(const softray_frame* fr, int n)
     int s = fr->start_row < 0 ? 0 : fr->start_row; if (s > fr->height - 1) s = fr->height - 1;
     int e = fr->end_row < 0 ? 0 : fr->end_row;     if (e > fr->height - 1) e = fr->height - 1;
     const int rows = e - s + 1;
-    int bh = rows / (n * 16);                         // ~16 bands per device: background rows spread evenly
+    int bh = rows / (n * 64);                         // ~64 bands per device: expensive rows come in strips, spread them
     bh = bh / 4 * 4;                                  // whole 4-row tiles
     return bh < 4 ? 4 : bh;
 }

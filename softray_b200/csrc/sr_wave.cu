@@ -976,7 +976,7 @@ cudaError_t wave_render(const DevFrame& f, const DevScene& sc, const DevInstance
     if (cap_samples / per_tile == 0) return cudaErrorInvalidValue;
     long long n_chunks = (n_tiles * per_tile + cap_samples - 1) / cap_samples;
     const bool profiling = prof != nullptr && prof->on;
-    const bool two = side_stream != nullptr && !profiling && env_occ("SOFTRAY_WAVE_STREAMS", 2) >= 2 && n_tiles * per_tile >= (1u << 20);
+    const bool two = side_stream != nullptr && !profiling && env_occ("SOFTRAY_WAVE_STREAMS", 2) >= 2 && n_tiles * per_tile >= (1u << 18);
     if (two && n_chunks < 2) n_chunks = 2;
     if (host) {     // the last chunk's copy is exposed: more, smaller chunks -- but not below 4 M samples (config3 as 8 chunks: 7.2 -> 8.5 ms)
         long long want = n_tiles * per_tile / (1ll << 22);

@@ -37,8 +37,10 @@ def rows_of_rank(height, n_ranks, band_height, rank, start_row=None, end_row=Non
     return rows[((rows - s) // band_height) % n_ranks == rank]
 
 
-def default_band_height(height, n_ranks, target_bands_per_rank=16, tile_rows=4):
-    """A multiple of the kernel's 4-row tile that gives every rank ~16 interleaved bands."""
+def default_band_height(height, n_ranks, target_bands_per_rank=64, tile_rows=4):
+    """A multiple of the kernel's 4-row tile that gives every rank ~64 interleaved bands: expensive rows come in
+    strips (config3's grazing shadow rays sit in a few dozen rows near the horizon), and a strip must not fall to one
+    or two ranks (16 bands per rank: config3 3.0 ms on 8 GPUs, slower than on 4)."""
     if n_ranks <= 1:
         return 0
     bh = height // (n_ranks * target_bands_per_rank)
