@@ -847,8 +847,9 @@ size_t wave_buffer_bytes(uint32_t cap_samples, int max_depth_slots, WaveLayout* 
     lay->slot_escaped = take(S * (size_t)max_depth_slots * sizeof(uint32_t));
     lay->sample_state = take(S);
     lay->sample_id = take(S * sizeof(int32_t));
-    lay->ref0 = take(S * sizeof(RefRay));
-    lay->ref1 = take(S * sizeof(RefRay));
+    const size_t n_ref = max_depth_slots > 1 ? S : 1;         // (no reflection: no reflection-ray lists)
+    lay->ref0 = take(n_ref * sizeof(RefRay));
+    lay->ref1 = take(n_ref * sizeof(RefRay));
     lay->shadow = take(S * (size_t)max_depth_slots * sizeof(ShadowItem));
     lay->fallback = take(S * sizeof(uint32_t));
     lay->walk_list = take(S * (size_t)max_depth_slots * sizeof(uint32_t));
