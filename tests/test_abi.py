@@ -69,6 +69,12 @@ def test_no_device_means_loud_failure(L):
     with pytest.raises(lib.SoftRayError) as e:
         lib.Context(0)
     assert e.value.code == abi.E_NO_DEVICE
+    # ... and so does the group context (softray_create_multi): no device, no context, no fallback
+    assert L.softray_create_multi(0, C.byref(h)) == abi.E_NO_DEVICE and not h.value
+    with pytest.raises(lib.SoftRayError) as e:
+        lib.Context(n_devices=0)
+    assert e.value.code == abi.E_NO_DEVICE
+    assert L.softray_device_count(None) == 0
 
 
 def test_null_arguments_are_rejected(L):
