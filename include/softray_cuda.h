@@ -250,7 +250,11 @@ int  softray_render(softray_ctx* ctx, const softray_scene* scene, const softray_
 /* Device-buffer entry point (the timed "inputs already resident" path and the multi-GPU path:
  * the band stays in HBM for the NCCL gather).  d_pixels/d_hit_ids are device pointers on the
  * context's device with the same full-frame indexing; `stream` is a cudaStream_t (0 = the
- * context's own stream).  Asynchronous with respect to the host unless stats != NULL. */
+ * context's own stream).  Asynchronous with respect to the host unless stats != NULL (or the context is a group).
+ * Frames of one context share its per-frame device scratch: a frame enqueued on another stream than the previous
+ * one first waits (on the device) for that one, so consecutive asynchronous calls never race; no row of the frame
+ * is this call's (start_row > end_row after the clamp, or a band set without rows): nothing is launched and *stats
+ * is all zero. */
 int  softray_render_device(softray_ctx* ctx, const softray_scene* scene, const softray_frame* frame,
                            uint32_t* d_pixels_argb, int32_t* d_hit_ids, void* stream,
                            softray_stats* stats);
