@@ -213,3 +213,51 @@ def test_model_from_arrays_normalises():
     assert m.bbox_min.tolist() == [-0.5, -0.25, -0.125] and m.bbox_max.tolist() == [0.5, 0.25, 0.125]
     raw = oracle.model_from_arrays(v, t, normalise=False)
     assert raw.bbox_max.tolist() == [4, 2, 1]
+
+
+def test_oracle_column_window_is_the_same_pixels(obj_mesh):
+    """The test-only column window (orc_options.col_start/col_end) traces exactly the pixels of the window: same
+    colours, ids and ray counts as the same pixels of the whole rows; nothing outside the window is written."""
+    import numpy as np
+
+    import oracle
+    from tests.util import scenario
+
+    orc = oracle.Scene([obj_mesh])
+    p = scenario(resolution=64, shadows=True, shadow_samples=5, sub_pixel_res=2, start_row=20, end_row=41)
+    full = orc.render(p, want_ids=True)
+    px = np.full((64, 64), 0xDEADBEEF, dtype=np.uint32)
+    win = orc.render(p, options=oracle.default_options(col_start=17, col_end=40), want_ids=True, pixels=px)
+    assert (win["pixels"][20:42, 17:41] == full["pixels"][20:42, 17:41]).all()
+    assert (win["ids"][20:42, 17:41] == full["ids"][20:42, 17:41]).all()
+    outside = np.ones((64, 64), dtype=bool)
+    outside[20:42, 17:41] = False
+    assert (px[outside] == 0xDEADBEEF).all()
+    assert win["stats"].rays_primary == 22 * 24 * 4 and full["stats"].rays_primary == 22 * 64 * 4
+    # an empty window produces nothing
+    none = orc.render(p, options=oracle.default_options(col_start=50, col_end=40))
+    assert none["stats"].rays == 0
+
+
+def test_multiply_high_division_constants():
+    """The stage kernels divide ray indices by per-frame constants with one multiply-high and a shift (FastDiv,
+    sr_types.h; constants from make_fastdiv, sr_api.cu: p = 31 + ceil(log2 d), mul = ceil(2^p / d), shift = p - 32).
+    The same construction, checked exhaustively near every boundary for the divisors frames use."""
+    def make(d):
+        if d == 1:
+            return None
+        lg = (d - 1).bit_length()
+        p = 31 + lg
+        return ((1 << p) + d - 1) // d, p - 32
+
+    for d in [1, 2, 3, 4, 5, 7, 9, 16, 25, 32, 36, 49, 64, 81, 128, 288, 960, 1000, 2048, 32 * 64, 7680, 65535, 1 << 20, (1 << 20) + 7]:
+        c = make(d)
+        ns = {0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 31) - 1, (1 << 31) - d, 123456789, 987654321}
+        ns |= {k * d + off for k in (3, 1000, (1 << 31) // d - 1) for off in (-1, 0, 1)}
+        for n in ns:
+            if not 0 <= n < (1 << 31):
+                continue
+            if c is not None:
+                assert c[0] < (1 << 32)
+            q = n if c is None else ((n * c[0]) >> 32) >> c[1]
+            assert q == n // d, (n, d)
